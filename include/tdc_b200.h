@@ -1,0 +1,170 @@
+/*
+ * tdc_b200.h — C ABI of libtdc_b200.so: hand-written sm_100a CUDA kernels for the
+ * Temporal Dynamic Context (TDC) compression path of Hoar012/TDC-Video.
+ *
+ * The reference has no FFI layer of its own: its boundary for this path is a set of
+ * nn.Module attributes called from tdc/cambrian_arch.py.  Each entry point below
+ * names the reference call it stands in for (file:line under the reference repo);
+ * INTEGRATION.md shows the Python-side binding (ctypes) a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all calls are stream-ordered and asynchronous, never synchronise, and never
+ *     allocate after tdc_create / tdc_load_weights (graph-capturable);
+ *   - the caller owns inputs, outputs and the workspace; the handle owns only its
+ *     re-packed copy of the weights;
+ *   - return value: TDC_OK (0) or a negative tdc_status; tdc_last_error() gives text.
+ *   - eval-mode only (dropout = identity), exactly like every reference call site
+ *     on the inference path.
+ */
+#ifndef TDC_B200_H_
+#define TDC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDC_B200_ABI_VERSION 1
+
+typedef enum tdc_status {
+  TDC_OK = 0,
+  TDC_EINVAL = -1,   /* bad shape / alignment / null pointer / unsupported geometry */
+  TDC_ECUDA = -2,    /* a CUDA runtime or driver call failed */
+  TDC_ENOMEM = -3,   /* device allocation failed (create / load_weights only) */
+  TDC_ESTATE = -4,   /* call made in the wrong state (e.g. forward before load_weights) */
+  TDC_EWORKSPACE = -5 /* workspace smaller than tdc_workspace_bytes() */
+} tdc_status;
+
+typedef enum tdc_dtype {
+  TDC_BF16 = 0,
+  TDC_F16 = 1,
+  TDC_F32 = 2
+} tdc_dtype;
+
+typedef void* tdc_stream_t; /* cudaStream_t */
+typedef struct tdc_handle tdc_handle;
+
+/* Geometry of the Q-Former + projections.  Mirrors the BertConfig fields the
+ * reference sets in tdc/cambrian_arch.py:403-424 (init_Qformer) plus the widths of
+ * vision_proj / query_proj (cambrian_arch.py:483-484). */
+typedef struct tdc_config {
+  int32_t hidden;            /* BertConfig.hidden_size (768); must be heads*64 */
+  int32_t heads;             /* num_attention_heads (12); head size is fixed at 64 */
+  int32_t intermediate;      /* intermediate_size (3072) */
+  int32_t layers;            /* num_hidden_layers (12) */
+  int32_t cross_freq;        /* cross_attention_freq (2): cross-attention in layers i % cross_freq == 0 */
+  int32_t d_enc;             /* encoder_width: width of the frame / segment tokens */
+  int32_t d_out;             /* vision_proj out_features (LLM hidden size); 0 = no vision_proj */
+  int32_t vocab;             /* word-embedding rows (30522); 0 = text input unsupported */
+  int32_t max_pos;           /* position-embedding rows (512) */
+  float ln_eps;              /* layer_norm_eps (1e-12) */
+  int32_t gemm_cta_group;    /* 0 = default, 1 = single-CTA tcgen05 tiles, 2 = CTA-pair tiles */
+  int32_t reserved[5];
+} tdc_config;
+
+/* One reference tensor (as stored in the reference state_dict, row-major). */
+typedef struct tdc_tensor {
+  const char* name;   /* state_dict key relative to `Qformer.bert.` or a sibling name, see DESIGN.md */
+  const void* data;   /* device pointer */
+  int32_t dtype;      /* tdc_dtype */
+  int32_t ndim;
+  int64_t shape[4];
+} tdc_tensor;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+/* replaces: BertLMHeadModel(config) construction, cambrian_arch.py:403-424 */
+int tdc_create(tdc_handle** out, const tdc_config* cfg);
+int tdc_destroy(tdc_handle* h);
+const char* tdc_last_error(const tdc_handle* h); /* h may be NULL: last error of failed create */
+int tdc_abi_version(void);
+
+/* replaces: load_state_dict of `model.Qformer.bert.*`, `model.vision_proj.*`
+ * (reference checkpoint layout).  Tensors are converted to the
+ * library's own bf16 / fp32 buffers on `stream`; missing optional tensors
+ * (text FFN, embeddings, vision_proj) disable the corresponding feature. */
+int tdc_load_weights(tdc_handle* h, const tdc_tensor* tensors, int32_t count, tdc_stream_t stream);
+
+/* ---- the hot path --------------------------------------------------------------- */
+/* Bytes of workspace tdc_qformer_forward / tdc_compress need for `rows` rows. */
+size_t tdc_workspace_bytes(const tdc_handle* h, int32_t rows, int32_t kv_len, int32_t num_query, int32_t num_text);
+
+/* replaces: Qformer.bert(input_ids=, query_embeds=, encoder_hidden_states=,
+ *           encoder_attention_mask=, use_cache=False, return_dict=True).last_hidden_state
+ *           — tdc/cambrian_arch.py:1653-1662, tdc/Qformer.py:804-965.
+ *   query_embeds   [n_query_sets, K, hidden]   (query_dtype)
+ *   query_set      [rows] int32 or NULL        row -> query set (NULL: row r uses set r)
+ *   input_ids      [n_text_sets, T] int64 or NULL (T == 0)
+ *   text_set       [rows] int32 or NULL        row -> text set (NULL: row r uses set r)
+ *   enc            [rows, L, d_enc]            (enc_dtype) encoder_hidden_states
+ *   kv_len         [rows] int32 or NULL        valid KV tokens per row (NULL: all L; the
+ *                                              reference always passes all-ones masks)
+ *   out_hidden     [rows, K+T, hidden]         (out_dtype) last_hidden_state
+ */
+int tdc_qformer_forward(tdc_handle* h, const void* query_embeds, int32_t query_dtype, const int32_t* query_set,
+                        const int64_t* input_ids, const int32_t* text_set, const void* enc, int32_t enc_dtype,
+                        const int32_t* kv_len, int32_t rows, int32_t kv_tokens, int32_t num_query, int32_t num_text,
+                        void* out_hidden, int32_t out_dtype, void* workspace, size_t workspace_bytes,
+                        tdc_stream_t stream);
+
+/* replaces: F.normalize(vision_proj(last_hidden_state[:, :K]), dim=-1)
+ *           — tdc/cambrian_arch.py:1664-1667.
+ *   hidden [rows, tokens_per_row, hidden] (hidden_dtype); the first num_query tokens of
+ *   every row are projected; out [rows, num_query, d_out] (out_dtype), unit L2 norm. */
+int tdc_proj_norm(tdc_handle* h, const void* hidden, int32_t hidden_dtype, int32_t rows, int32_t tokens_per_row,
+                  int32_t num_query, void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes,
+                  tdc_stream_t stream);
+
+/* Fused convenience entry: Q-Former + vision_proj + L2-normalise for all rows of a
+ * video at once (the reference runs <= 7 rows per call from a Python loop,
+ * cambrian_arch.py:1603-1692).  Arguments as tdc_qformer_forward; out is
+ * [rows, K, d_out] (out_dtype). */
+int tdc_compress(tdc_handle* h, const void* query_embeds, int32_t query_dtype, const int32_t* query_set,
+                 const int64_t* input_ids, const int32_t* text_set, const void* enc, int32_t enc_dtype,
+                 const int32_t* kv_len, int32_t rows, int32_t kv_tokens, int32_t num_query, int32_t num_text,
+                 void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes, tdc_stream_t stream);
+
+/* ---- small dense helpers on the same path ---------------------------------------- */
+/* replaces: nn.Linear forward — query_proj / audio_proj / vision_proj as plain callables
+ * (cambrian_arch.py:1613,1638,1665).  y[m, n] = x[m, k] . w[n, k]^T + bias.
+ * x, w bf16; bias fp32 or NULL; y bf16 (out_dtype TDC_BF16) or fp32 (TDC_F32). */
+int tdc_linear(const void* x, const void* w, const float* bias, void* y, int32_t m, int32_t n, int32_t k,
+               int32_t out_dtype, int32_t gelu, int32_t cta_group, tdc_stream_t stream);
+
+/* replaces: mm_projector = Linear -> GELU(erf) -> Linear (cambrian_arch.py:65-69,1149-1150;
+ * tdc/multimodal_projector/builder.py:40-47).  x [m, d_in] bf16, w0 [d_mid, d_in], w1 [d_out, d_mid] bf16,
+ * biases fp32, mid = caller scratch [m, d_mid] bf16, y [m, d_out] bf16. */
+int tdc_gelu_mlp(const void* x, const void* w0, const float* b0, const void* w1, const float* b1, void* mid, void* y,
+                 int32_t m, int32_t d_in, int32_t d_mid, int32_t d_out, tdc_stream_t stream);
+
+/* replaces: F.adaptive_avg_pool1d(key_frame.permute(2,0,1), K).permute(1,2,0)
+ *           — tdc/cambrian_arch.py:1633-1637.  frames [n, tokens, d] (dtype) -> out [n, K, d] bf16. */
+int tdc_avg_pool_tokens(const void* frames, int32_t dtype, int32_t n, int32_t tokens, int32_t d, int32_t num_query,
+                        void* out_bf16, tdc_stream_t stream);
+
+/* dtype conversion used by the host wrapper (fp32 / fp16 -> bf16 and back) */
+int tdc_convert(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t count, tdc_stream_t stream);
+
+/* ---- instrumentation ------------------------------------------------------------- */
+/* Per-kernel-class device time, measured with CUDA events on the launching stream when
+ * profiling is on.  Classes: see TDC_K_* below. */
+enum {
+  TDC_K_KV_GEMM = 0,    /* cross-attention K/V projection GEMM (dominant kernel) */
+  TDC_K_QUERY_GEMM = 1, /* all query-side GEMMs */
+  TDC_K_ATTENTION = 2,  /* self + cross short-query attention */
+  TDC_K_ROWOPS = 3,     /* LayerNorm / embeddings / L2-normalise / converts */
+  TDC_K_COUNT = 4
+};
+int tdc_set_profiling(tdc_handle* h, int32_t enabled);
+/* Sums (ms) and launch counts since the last reset; synchronises the recorded events. */
+int tdc_get_profile(tdc_handle* h, int32_t kernel_class, double* total_ms, int64_t* launches);
+int tdc_reset_profile(tdc_handle* h);
+/* Total kernels launched by this handle since creation (for launch accounting). */
+int64_t tdc_launch_count(const tdc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDC_B200_H_ */

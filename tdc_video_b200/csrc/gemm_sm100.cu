@@ -1,0 +1,378 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C = epilogue(A . W^T), bf16 in, fp32 accumulate.
+//
+// This is the kernel behind every dense contraction on the TDC path — the
+// cross-attention K/V projections of all Q-Former layers at once (reference:
+// tdc/Qformer.py:129-130,186-187 — 74-87 % of the path's FLOPs), the self-attention
+// QKV / output projections (Qformer.py:125,285-289), the FFN (Qformer.py:349-375),
+// vision_proj / query_proj / audio_proj (tdc/cambrian_arch.py:483-484,180-181) and
+// the GELU-MLP projector (cambrian_arch.py:65-69).
+//
+// Design (B200-first, not a translation of anything in the reference, which only
+// calls cuBLAS through nn.Linear):
+//   * persistent grid: one CTA (CG=1) or one CTA pair (CG=2, cta_group::2) per SM / TPC,
+//     static round-robin over output tiles, N fastest so that the concurrently
+//     running tiles share a handful of A row-panels while W stays L2-resident;
+//   * warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
+//     tcgen05.mma issuer, warps 2-5 = epilogue (one TMEM lane quadrant each);
+//   * STAGES-deep smem ring of 128B-swizzled K-major tiles (A 128x64, W BLOCK_N/CG x64)
+//     with full/empty mbarriers; tcgen05.commit releases a slot as soon as the MMAs
+//     that read it have retired;
+//   * fp32 accumulators in TMEM, double buffered (2 x BLOCK_N columns) so the
+//     epilogue of tile i overlaps the mainloop of tile i+1;
+//   * epilogue fused into the drain: +bias, exact-erf GELU, fp32 residual add,
+//     bf16 / fp32 stores straight from registers (each thread owns one output row).
+#include "tdc_gemm.cuh"
+#include "tdc_ptx.cuh"
+#include "tdc_b200.h"
+
+#include <mutex>
+
+namespace tdc {
+
+namespace {
+
+constexpr int kBlockM = 128;  // rows per CTA (UMMA M = 128 * CG)
+constexpr int kBlockK = 64;   // one 128-byte swizzle span of bf16
+constexpr int kUmmaK = 16;
+constexpr int kNumThreads = 192;
+constexpr int kAccStages = 2;
+
+struct EpilogueArgs {
+  void* out;
+  long long ldo;
+  const float* bias;
+  const float* resid;
+  long long ldr;
+  int mode;
+};
+
+template <int CG, int BLOCK_N, int STAGES>
+struct SmemLayout {
+  static constexpr int kBRows = BLOCK_N / CG;
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = kBRows * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarrierOffset = STAGES * kStageBytes;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem base ptr
+  static constexpr int kBarrierBytes = (2 * STAGES + 2 * kAccStages) * 8 + 16;
+  static constexpr int kTotalBytes = kBarrierOffset + kBarrierBytes + 1024;  // + manual 1024 B alignment slack
+};
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_store_32(const uint32_t (&v)[32], long long row, int col0, int n,
+                                                  const EpilogueArgs& e) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = col0 + g * 8;
+    if (col >= n) break;
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
+    if (e.bias != nullptr) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col + 4));
+      x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+      x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+    }
+    if (MODE == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
+    }
+    if (MODE == EPI_BIAS_RESID_F32) {
+      if (e.resid != nullptr) {
+        const float4 r0 = *reinterpret_cast<const float4*>(e.resid + row * e.ldr + col);
+        const float4 r1 = *reinterpret_cast<const float4*>(e.resid + row * e.ldr + col + 4);
+        x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
+        x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
+      }
+      float* o = reinterpret_cast<float*>(e.out) + row * e.ldo + col;
+      *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
+    } else {
+      uint4 pk;
+      pk.x = pack_bf16x2(x[0], x[1]);
+      pk.y = pack_bf16x2(x[2], x[3]);
+      pk.z = pack_bf16x2(x[4], x[5]);
+      pk.w = pack_bf16x2(x[6], x[7]);
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) + row * e.ldo + col;
+      *reinterpret_cast<uint4*>(o) = pk;
+    }
+  }
+}
+
+template <int CG, int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kNumThreads, 1)
+tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int m, int n,
+                int k, EpilogueArgs epi) {
+  using L = SmemLayout<CG, BLOCK_N, STAGES>;
+  constexpr uint32_t kTmemCols = kAccStages * BLOCK_N;  // 512 (BLOCK_N=256) or 256
+  constexpr uint32_t kIdesc = make_idesc_bf16_f32(kBlockM * CG, BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment; dynamic smem only promises 16.
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarrierOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + kAccStages);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = (cta_rank == 0);
+
+  const int tile_m_rows = kBlockM * CG;
+  const int num_m_tiles = (m + tile_m_rows - 1) / tile_m_rows;
+  const int num_n_tiles = (n + BLOCK_N - 1) / BLOCK_N;
+  const long long num_tiles = static_cast<long long>(num_m_tiles) * num_n_tiles;
+  const int num_kb = (k + kBlockK - 1) / kBlockK;
+  const long long first_tile = blockIdx.x / CG;
+  const long long tile_stride = gridDim.x / CG;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4 * CG);  // one elected lane per epilogue warp (of both CTAs)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc<CG>(tmem_base_smem, kTmemCols);
+    tmem_relinquish<CG>();
+  }
+  tc_fence_before_sync();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = first_tile; tile < num_tiles; tile += tile_stride) {
+        const int tm = static_cast<int>(tile / num_n_tiles);
+        const int tn = static_cast<int>(tile % num_n_tiles);
+        const int row_a = tm * tile_m_rows + static_cast<int>(cta_rank) * kBlockM;
+        const int row_w = tn * BLOCK_N + static_cast<int>(cta_rank) * L::kBRows;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          if (CG == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+            tma_load_2d(sa, &map_a, &full_bar[stage], kb * kBlockK, row_a);
+            tma_load_2d(sb, &map_w, &full_bar[stage], kb * kBlockK, row_w);
+          } else {
+            // both CTAs' bytes are credited to the leader's barrier
+            if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+            tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * kBlockK, row_a);
+            tma_load_2d_pair(sb, &map_w, &full_bar[stage], kb * kBlockK, row_w);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread, leader CTA only) =====================
+    if (lane == 0 && is_leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long tile = first_tile; tile < num_tiles; tile += tile_stride) {
+        mbar_wait<CG == 2>(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint64_t desc_a = make_kmajor_sw128_desc(sa);
+          const uint64_t desc_b = make_kmajor_sw128_desc(sa + L::kABytes);
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
+            // advance 16 bf16 = 32 B along K inside the swizzle span: +2 in the (addr >> 4) field
+            umma_f16<CG>(d_tmem, desc_a + 2u * kk, desc_b + 2u * kk, kIdesc, (kb | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit<CG>(&empty_bar[stage]);  // slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit<CG>(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const uint32_t quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = first_tile; tile < num_tiles; tile += tile_stride) {
+      const int tm = static_cast<int>(tile / num_n_tiles);
+      const int tn = static_cast<int>(tile % num_n_tiles);
+      const long long row = static_cast<long long>(tm) * tile_m_rows + cta_rank * kBlockM + quad * 32 + lane;
+      const int col_base = tn * BLOCK_N;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + ((quad * 32u) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + c * 32, v);
+        tmem_ld_wait();
+        if (row < m) {
+          const int col0 = col_base + c * 32;
+          if (epi.mode == EPI_BIAS_BF16) epilogue_store_32<EPI_BIAS_BF16>(v, row, col0, n, epi);
+          else if (epi.mode == EPI_BIAS_GELU_BF16) epilogue_store_32<EPI_BIAS_GELU_BF16>(v, row, col0, n, epi);
+          else epilogue_store_32<EPI_BIAS_RESID_F32>(v, row, col0, n, epi);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 1) mbar_arrive(&tmem_empty_bar[acc]);
+        else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+      }
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  // ===================== teardown =====================
+  tc_fence_before_sync();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after_sync();
+    tmem_dealloc<CG>(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] (pitch ld elements) -> tiles of box_rows x 64 with 128B swizzle.
+bool make_tensor_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return false;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sms;
+}
+
+template <int CG, int BLOCK_N, int STAGES>
+int launch_variant(const GemmProblem& p, cudaStream_t stream, const char** err) {
+  using L = SmemLayout<CG, BLOCK_N, STAGES>;
+  CUtensorMap map_a, map_w;
+  if (!make_tensor_map(&map_a, p.a, p.m, p.k, p.lda, kBlockM) ||
+      !make_tensor_map(&map_w, p.w, p.n, p.k, p.ldw, L::kBRows)) {
+    if (err) *err = "cuTensorMapEncodeTiled failed (pointer/pitch alignment?)";
+    return TDC_ECUDA;
+  }
+  auto kernel = tdc_gemm_kernel<CG, BLOCK_N, STAGES>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotalBytes) != cudaSuccess) {
+      if (err) *err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
+      return TDC_ECUDA;
+    }
+    attr_set = true;
+  }
+  const long long tiles = static_cast<long long>((p.m + kBlockM * CG - 1) / (kBlockM * CG)) *
+                          ((p.n + BLOCK_N - 1) / BLOCK_N);
+  long long clusters = num_sms() / CG;
+  if (tiles < clusters) clusters = tiles;
+  EpilogueArgs e{p.out, p.ldo, p.bias, p.resid, p.ldr, p.mode};
+
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * CG));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = L::kTotalBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t rc = cudaLaunchKernelEx(&cfg, kernel, map_a, map_w, p.m, p.n, p.k, e);
+  if (rc != cudaSuccess) {
+    if (err) *err = cudaGetErrorString(rc);
+    return TDC_ECUDA;
+  }
+  return TDC_OK;
+}
+
+}  // namespace
+
+int gemm_launch(const GemmProblem& p, cudaStream_t stream, const char** err) {
+  if (p.m <= 0 || p.n <= 0 || p.k <= 0) {
+    if (err) *err = "gemm: empty problem";
+    return TDC_EINVAL;
+  }
+  if ((p.k % 8) != 0 || (p.n % 8) != 0 || (p.lda % 8) != 0 || (p.ldw % 8) != 0 || (p.ldo % 4) != 0 ||
+      (reinterpret_cast<uintptr_t>(p.a) & 15) || (reinterpret_cast<uintptr_t>(p.w) & 15) ||
+      (reinterpret_cast<uintptr_t>(p.out) & 15)) {
+    if (err) *err = "gemm: K, N and pitches must be multiples of 8 elements and pointers 16-byte aligned";
+    return TDC_EINVAL;
+  }
+  if (p.mode != EPI_BIAS_RESID_F32 && (p.ldo % 8) != 0) {
+    if (err) *err = "gemm: bf16 output pitch must be a multiple of 8 elements";
+    return TDC_EINVAL;
+  }
+  if (p.mode < 0 || p.mode > EPI_BIAS_RESID_F32) {
+    if (err) *err = "gemm: unknown epilogue mode";
+    return TDC_EINVAL;
+  }
+  int cg = p.cta_group == 0 ? 1 : p.cta_group;
+  if (p.n <= 128) {
+    // narrow outputs (small test geometries): single-CTA 128x128 tiles
+    return launch_variant<1, 128, 6>(p, stream, err);
+  }
+  if (cg == 2) return launch_variant<2, 256, 6>(p, stream, err);
+  return launch_variant<1, 256, 4>(p, stream, err);
+}
+
+}  // namespace tdc

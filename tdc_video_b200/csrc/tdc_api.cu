@@ -1,0 +1,693 @@
+// C ABI of libtdc_b200.so (see include/tdc_b200.h): weight re-packing and the launch
+// sequence of the batched Q-Former forward.  No torch types, no hidden allocations in the
+// forward calls, no host<->device synchronisation.
+//
+// Launch sequence for `rows` rows (one row = one dynamic frame = one Q-Former batch element
+// of the reference, tdc/cambrian_arch.py:1625-1662), K queries, T text tokens, L KV tokens:
+//
+//   [convert enc -> bf16]                                                   (only if not bf16)
+//   KV   = enc . Wkv^T + b        one GEMM for all cross layers, N = 2*H*n_cross     (Qformer.py:186-187)
+//   h    = LN(embeddings)                                                            (Qformer.py:78-108)
+//   for each layer:
+//     qkv  = h . Wqkv^T + b                                                          (Qformer.py:125-198)
+//     ctx  = softmax(q k^T / 8) v        over the row's K+T tokens                   (Qformer.py:205-268)
+//     h    = LN(ctx . Wo^T + b + h)                                                  (Qformer.py:285-289)
+//     even layers, query tokens only:                                                (Qformer.py:430-447)
+//       qc = h . Wq^T + b ; ctx = softmax(qc KV_k^T / 8) KV_v ; h = LN(ctx . Wo^T + b + h)
+//     query tokens: h = LN(gelu(h W1^T + b1) W2^T + b2 + h)   (intermediate_query/output_query, :449-454)
+//     text  tokens: same with intermediate/output                                    (:455-462)
+//   out  = h  |  F.normalize(h[:, :K] . Wvp^T + b)                          (cambrian_arch.py:1664-1667)
+#include "tdc_b200.h"
+#include "tdc_gemm.cuh"
+#include "tdc_kernels.cuh"
+
+#include <cstring>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+using namespace tdc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct LayerW {
+  __nv_bfloat16* w_qkv = nullptr; float* b_qkv = nullptr;
+  __nv_bfloat16* w_ao = nullptr; float* b_ao = nullptr; float* ln_a_g = nullptr; float* ln_a_b = nullptr;
+  int cross_index = -1;  // >= 0: this layer has cross-attention; slot in the fused K/V weight
+  __nv_bfloat16* w_cq = nullptr; float* b_cq = nullptr;
+  __nv_bfloat16* w_co = nullptr; float* b_co = nullptr; float* ln_c_g = nullptr; float* ln_c_b = nullptr;
+  __nv_bfloat16* w_fq1 = nullptr; float* b_fq1 = nullptr; __nv_bfloat16* w_fq2 = nullptr; float* b_fq2 = nullptr;
+  float* ln_fq_g = nullptr; float* ln_fq_b = nullptr;
+  __nv_bfloat16* w_ft1 = nullptr; float* b_ft1 = nullptr; __nv_bfloat16* w_ft2 = nullptr; float* b_ft2 = nullptr;
+  float* ln_ft_g = nullptr; float* ln_ft_b = nullptr;
+};
+
+struct ProfileClass {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+  size_t used = 0;
+};
+
+}  // namespace
+
+struct tdc_handle {
+  tdc_config cfg{};
+  int n_cross = 0;
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  std::vector<LayerW> layers;
+  __nv_bfloat16* w_ckv = nullptr; float* b_ckv = nullptr;  // [n_cross*2H, d_enc]
+  float* word_emb = nullptr; float* pos_emb = nullptr; float* ln_e_g = nullptr; float* ln_e_b = nullptr;
+  __nv_bfloat16* w_vp = nullptr; float* b_vp = nullptr;
+  bool loaded = false, have_text_ffn = false, have_embeddings = false, have_vp = false;
+  std::vector<uint8_t> seen;  // per expected tensor
+  std::string last_error;
+  bool profiling = false;
+  ProfileClass prof[TDC_K_COUNT];
+  int64_t launches = 0;
+};
+
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+
+int fail(tdc_handle* h, int code, const std::string& msg) {
+  if (h) h->last_error = msg;
+  return code;
+}
+
+// ---- weight arena -------------------------------------------------------------------
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  template <typename T> T* take(size_t count) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += align_up(count * sizeof(T));
+    return p;
+  }
+};
+
+void carve_weights(tdc_handle* h, uint8_t* base, size_t* total) {
+  const tdc_config& c = h->cfg;
+  const size_t H = c.hidden, I = c.intermediate, E = c.d_enc;
+  Carver cv{base};
+  h->w_ckv = cv.take<__nv_bfloat16>(static_cast<size_t>(h->n_cross) * 2 * H * E);
+  h->b_ckv = cv.take<float>(static_cast<size_t>(h->n_cross) * 2 * H);
+  h->ln_e_g = cv.take<float>(H);
+  h->ln_e_b = cv.take<float>(H);
+  if (c.vocab > 0) {
+    h->word_emb = cv.take<float>(static_cast<size_t>(c.vocab) * H);
+    h->pos_emb = cv.take<float>(static_cast<size_t>(c.max_pos) * H);
+  }
+  if (c.d_out > 0) {
+    h->w_vp = cv.take<__nv_bfloat16>(static_cast<size_t>(c.d_out) * H);
+    h->b_vp = cv.take<float>(c.d_out);
+  }
+  int cross = 0;
+  for (int l = 0; l < c.layers; ++l) {
+    LayerW& w = h->layers[l];
+    w.w_qkv = cv.take<__nv_bfloat16>(3 * H * H); w.b_qkv = cv.take<float>(3 * H);
+    w.w_ao = cv.take<__nv_bfloat16>(H * H); w.b_ao = cv.take<float>(H);
+    w.ln_a_g = cv.take<float>(H); w.ln_a_b = cv.take<float>(H);
+    if (l % c.cross_freq == 0) {
+      w.cross_index = cross++;
+      w.w_cq = cv.take<__nv_bfloat16>(H * H); w.b_cq = cv.take<float>(H);
+      w.w_co = cv.take<__nv_bfloat16>(H * H); w.b_co = cv.take<float>(H);
+      w.ln_c_g = cv.take<float>(H); w.ln_c_b = cv.take<float>(H);
+    }
+    w.w_fq1 = cv.take<__nv_bfloat16>(I * H); w.b_fq1 = cv.take<float>(I);
+    w.w_fq2 = cv.take<__nv_bfloat16>(H * I); w.b_fq2 = cv.take<float>(H);
+    w.ln_fq_g = cv.take<float>(H); w.ln_fq_b = cv.take<float>(H);
+    if (c.vocab > 0) {
+      w.w_ft1 = cv.take<__nv_bfloat16>(I * H); w.b_ft1 = cv.take<float>(I);
+      w.w_ft2 = cv.take<__nv_bfloat16>(H * I); w.b_ft2 = cv.take<float>(H);
+      w.ln_ft_g = cv.take<float>(H); w.ln_ft_b = cv.take<float>(H);
+    }
+  }
+  *total = cv.off;
+}
+
+// A destination inside the arena for one named reference tensor.
+struct Slot {
+  void* dst = nullptr;
+  bool as_bf16 = false;
+  int64_t rows = 0, cols = 0;  // expected shape (cols == 0: 1-D of `rows`)
+  int group = 0;               // 0 core, 1 text FFN, 2 embeddings, 3 vision_proj
+};
+
+bool resolve_slot(tdc_handle* h, const std::string& name, Slot* s) {
+  const tdc_config& c = h->cfg;
+  const int64_t H = c.hidden, I = c.intermediate, E = c.d_enc;
+  auto W = [&](__nv_bfloat16* p, int64_t r, int64_t cc, int grp = 0) { *s = Slot{p, true, r, cc, grp}; return p != nullptr; };
+  auto V = [&](float* p, int64_t r, int grp = 0) { *s = Slot{p, false, r, 0, grp}; return p != nullptr; };
+  if (name == "vision_proj.weight") return W(h->w_vp, c.d_out, H, 3);
+  if (name == "vision_proj.bias") return V(h->b_vp, c.d_out, 3);
+  if (name == "embeddings.LayerNorm.weight") return V(h->ln_e_g, H);
+  if (name == "embeddings.LayerNorm.bias") return V(h->ln_e_b, H);
+  if (name == "embeddings.word_embeddings.weight") { *s = Slot{h->word_emb, false, c.vocab, H, 2}; return h->word_emb != nullptr; }
+  if (name == "embeddings.position_embeddings.weight") { *s = Slot{h->pos_emb, false, c.max_pos, H, 2}; return h->pos_emb != nullptr; }
+  const std::string pre = "encoder.layer.";
+  if (name.compare(0, pre.size(), pre) != 0) return false;
+  size_t dot = name.find('.', pre.size());
+  if (dot == std::string::npos) return false;
+  int l = 0;
+  for (size_t i = pre.size(); i < dot; ++i) {
+    if (name[i] < '0' || name[i] > '9') return false;
+    l = l * 10 + (name[i] - '0');
+  }
+  if (l < 0 || l >= c.layers) return false;
+  LayerW& w = h->layers[l];
+  const std::string rest = name.substr(dot + 1);
+  if (rest == "attention.self.query.weight") return W(w.w_qkv, H, H);
+  if (rest == "attention.self.key.weight") return W(w.w_qkv + H * H, H, H);
+  if (rest == "attention.self.value.weight") return W(w.w_qkv + 2 * H * H, H, H);
+  if (rest == "attention.self.query.bias") return V(w.b_qkv, H);
+  if (rest == "attention.self.key.bias") return V(w.b_qkv + H, H);
+  if (rest == "attention.self.value.bias") return V(w.b_qkv + 2 * H, H);
+  if (rest == "attention.output.dense.weight") return W(w.w_ao, H, H);
+  if (rest == "attention.output.dense.bias") return V(w.b_ao, H);
+  if (rest == "attention.output.LayerNorm.weight") return V(w.ln_a_g, H);
+  if (rest == "attention.output.LayerNorm.bias") return V(w.ln_a_b, H);
+  if (w.cross_index >= 0) {
+    const int64_t j = w.cross_index;
+    if (rest == "crossattention.self.query.weight") return W(w.w_cq, H, H);
+    if (rest == "crossattention.self.query.bias") return V(w.b_cq, H);
+    if (rest == "crossattention.self.key.weight") return W(h->w_ckv + (j * 2) * H * E, H, E);
+    if (rest == "crossattention.self.value.weight") return W(h->w_ckv + (j * 2 + 1) * H * E, H, E);
+    if (rest == "crossattention.self.key.bias") return V(h->b_ckv + (j * 2) * H, H);
+    if (rest == "crossattention.self.value.bias") return V(h->b_ckv + (j * 2 + 1) * H, H);
+    if (rest == "crossattention.output.dense.weight") return W(w.w_co, H, H);
+    if (rest == "crossattention.output.dense.bias") return V(w.b_co, H);
+    if (rest == "crossattention.output.LayerNorm.weight") return V(w.ln_c_g, H);
+    if (rest == "crossattention.output.LayerNorm.bias") return V(w.ln_c_b, H);
+  }
+  if (rest == "intermediate_query.dense.weight") return W(w.w_fq1, I, H);
+  if (rest == "intermediate_query.dense.bias") return V(w.b_fq1, I);
+  if (rest == "output_query.dense.weight") return W(w.w_fq2, H, I);
+  if (rest == "output_query.dense.bias") return V(w.b_fq2, H);
+  if (rest == "output_query.LayerNorm.weight") return V(w.ln_fq_g, H);
+  if (rest == "output_query.LayerNorm.bias") return V(w.ln_fq_b, H);
+  if (rest == "intermediate.dense.weight") return W(w.w_ft1, I, H, 1);
+  if (rest == "intermediate.dense.bias") return V(w.b_ft1, I, 1);
+  if (rest == "output.dense.weight") return W(w.w_ft2, H, I, 1);
+  if (rest == "output.dense.bias") return V(w.b_ft2, H, 1);
+  if (rest == "output.LayerNorm.weight") return V(w.ln_ft_g, H, 1);
+  if (rest == "output.LayerNorm.bias") return V(w.ln_ft_b, H, 1);
+  return false;
+}
+
+// Names every handle must receive (core) — used to detect an incomplete load.
+std::vector<std::string> expected_names(const tdc_handle* h, int group) {
+  std::vector<std::string> out;
+  const tdc_config& c = h->cfg;
+  auto wb = [&](const std::string& p) { out.push_back(p + ".weight"); out.push_back(p + ".bias"); };
+  if (group == 0) wb("embeddings.LayerNorm");
+  if (group == 2) { out.push_back("embeddings.word_embeddings.weight"); out.push_back("embeddings.position_embeddings.weight"); }
+  if (group == 3) wb("vision_proj");
+  for (int l = 0; l < c.layers; ++l) {
+    const std::string p = "encoder.layer." + std::to_string(l) + ".";
+    if (group == 0) {
+      wb(p + "attention.self.query"); wb(p + "attention.self.key"); wb(p + "attention.self.value");
+      wb(p + "attention.output.dense"); wb(p + "attention.output.LayerNorm");
+      if (l % c.cross_freq == 0) {
+        wb(p + "crossattention.self.query"); wb(p + "crossattention.self.key"); wb(p + "crossattention.self.value");
+        wb(p + "crossattention.output.dense"); wb(p + "crossattention.output.LayerNorm");
+      }
+      wb(p + "intermediate_query.dense"); wb(p + "output_query.dense"); wb(p + "output_query.LayerNorm");
+    }
+    if (group == 1) { wb(p + "intermediate.dense"); wb(p + "output.dense"); wb(p + "output.LayerNorm"); }
+  }
+  return out;
+}
+
+// ---- profiling ----------------------------------------------------------------------
+struct KernelScope {
+  tdc_handle* h;
+  cudaStream_t s;
+  cudaEvent_t stop = nullptr;
+  KernelScope(tdc_handle* h_, int cls, cudaStream_t s_, int n_launches = 1) : h(h_), s(s_) {
+    h->launches += n_launches;
+    if (!h->profiling) return;
+    ProfileClass& pc = h->prof[cls];
+    if (pc.used == pc.events.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      pc.events.emplace_back(a, b);
+    }
+    cudaEventRecord(pc.events[pc.used].first, s);
+    stop = pc.events[pc.used].second;
+    ++pc.used;
+  }
+  ~KernelScope() {
+    if (stop) cudaEventRecord(stop, s);
+  }
+};
+
+// ---- forward ------------------------------------------------------------------------
+struct Workspace {
+  __nv_bfloat16* enc_bf16;
+  __nv_bfloat16* kv;
+  float* h_f32;
+  __nv_bfloat16* h_bf16;
+  __nv_bfloat16* qkv;
+  __nv_bfloat16* ctx;
+  float* pre;
+  __nv_bfloat16* qc;
+  __nv_bfloat16* mid;
+  float* proj;
+  size_t bytes;
+};
+
+Workspace carve_workspace(const tdc_handle* h, uint8_t* base, long long rows, int L, int K, int T, bool enc_convert,
+                          bool with_proj) {
+  const tdc_config& c = h->cfg;
+  const size_t H = c.hidden, I = c.intermediate, n = static_cast<size_t>(K) + T, R = static_cast<size_t>(rows);
+  Carver cv{base};
+  Workspace w{};
+  w.enc_bf16 = enc_convert ? cv.take<__nv_bfloat16>(R * L * c.d_enc) : nullptr;
+  w.kv = cv.take<__nv_bfloat16>(R * L * 2 * H * h->n_cross);
+  w.h_f32 = cv.take<float>(R * n * H);
+  w.h_bf16 = cv.take<__nv_bfloat16>(R * n * H);
+  w.qkv = cv.take<__nv_bfloat16>(R * n * 3 * H);
+  w.ctx = cv.take<__nv_bfloat16>(R * n * H);
+  w.pre = cv.take<float>(R * n * H);
+  w.qc = cv.take<__nv_bfloat16>(R * K * H);
+  w.mid = cv.take<__nv_bfloat16>(R * std::max<size_t>(K, T) * I);
+  w.proj = with_proj ? cv.take<float>(R * K * c.d_out) : nullptr;
+  w.bytes = cv.off;
+  return w;
+}
+
+struct ForwardCall {
+  const void* query_embeds; int query_dtype; const int32_t* query_set;
+  const int64_t* input_ids; const int32_t* text_set;
+  const void* enc; int enc_dtype; const int32_t* kv_len;
+  long long rows; int L, K, T;
+  void* out; int out_dtype;   // hidden [rows, K+T, H] or compressed [rows, K, d_out]
+  bool compress;
+};
+
+#define TDC_TRY(expr)                                         \
+  do {                                                        \
+    const int rc_ = (expr);                                   \
+    if (rc_ != TDC_OK) return fail(h, rc_, err ? err : "?");  \
+  } while (0)
+
+int gemm(tdc_handle* h, int cls, cudaStream_t s, const void* a, long long lda, const void* w, long long ldw,
+         const float* bias, void* out, long long ldo, long long m, int n, int k, int mode, const float* resid,
+         long long ldr, const char** err) {
+  GemmProblem p;
+  p.a = a; p.lda = lda; p.w = w; p.ldw = ldw; p.bias = bias; p.out = out; p.ldo = ldo;
+  p.m = static_cast<int>(m); p.n = n; p.k = k; p.mode = mode; p.resid = resid; p.ldr = ldr;
+  p.cta_group = h->cfg.gemm_cta_group == 0 ? 2 : h->cfg.gemm_cta_group;
+  KernelScope ks(h, cls, s);
+  return gemm_launch(p, s, err);
+}
+
+// One batch of rows [row0, row0 + rows) of the call; all pointers in `f` are for the whole call.
+int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long rows, uint8_t* ws_base,
+                  cudaStream_t s) {
+  const tdc_config& c = h->cfg;
+  const int H = c.hidden, I = c.intermediate, K = f.K, T = f.T, L = f.L, n = K + T;
+  const char* err = nullptr;
+  const bool enc_convert = f.enc_dtype != TDC_BF16;
+  Workspace w = carve_workspace(h, ws_base, rows, L, K, T, enc_convert, f.compress);
+  const size_t esz = f.enc_dtype == TDC_F32 ? 4 : 2;
+  const uint8_t* enc_in = static_cast<const uint8_t*>(f.enc) + static_cast<size_t>(row0) * L * c.d_enc * esz;
+  const __nv_bfloat16* enc = reinterpret_cast<const __nv_bfloat16*>(enc_in);
+  if (enc_convert) {
+    KernelScope ks(h, TDC_K_ROWOPS, s);
+    TDC_TRY(convert_launch(enc_in, f.enc_dtype, w.enc_bf16, TDC_BF16, rows * L * c.d_enc, s, &err));
+    enc = w.enc_bf16;
+  }
+  const int* kv_len = f.kv_len ? f.kv_len + row0 : nullptr;
+  const int kvw = 2 * H * h->n_cross;  // K/V columns per KV token over all cross layers
+  const float scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
+
+  // 1. every cross layer's K and V for every KV token of every row: the dominant GEMM
+  if (h->n_cross > 0)
+    TDC_TRY(gemm(h, TDC_K_KV_GEMM, s, enc, c.d_enc, h->w_ckv, c.d_enc, h->b_ckv, w.kv, kvw, rows * L, kvw, c.d_enc,
+                 EPI_BIAS_BF16, nullptr, 0, &err));
+
+  // 2. embeddings + LayerNorm into the [query slab | text slab] layout
+  {
+    EmbedArgs e;
+    const size_t qsz = f.query_dtype == TDC_F32 ? 4 : 2;
+    e.query_embeds = f.query_set ? f.query_embeds
+                                 : static_cast<const uint8_t*>(f.query_embeds) + static_cast<size_t>(row0) * K * H * qsz;
+    e.query_dtype = f.query_dtype;
+    e.query_set = f.query_set ? f.query_set + row0 : nullptr;
+    e.input_ids = (T > 0) ? (f.text_set ? f.input_ids : f.input_ids + row0 * T) : nullptr;
+    e.text_set = f.text_set ? f.text_set + row0 : nullptr;
+    e.word_emb = h->word_emb; e.pos_emb = h->pos_emb; e.vocab = c.vocab;
+    e.gamma = h->ln_e_g; e.beta = h->ln_e_b; e.eps = c.ln_eps;
+    e.h_f32 = w.h_f32; e.h_bf16 = w.h_bf16;
+    e.rows = static_cast<int>(rows); e.num_query = K; e.num_text = T; e.hidden = H;
+    KernelScope ks(h, TDC_K_ROWOPS, s);
+    TDC_TRY(embed_layernorm_launch(e, s, &err));
+  }
+
+  const long long MQ = rows * K, MT = rows * T, MA = rows * n;
+  auto ln = [&](const float* g, const float* b, long long first, long long count) -> int {
+    KernelScope ks(h, TDC_K_ROWOPS, s);
+    return layernorm_launch(w.pre + first * H, H, g, b, c.ln_eps, w.h_f32 + first * H, w.h_bf16 + first * H, H, count,
+                            H, s, &err);
+  };
+
+  for (int l = 0; l < c.layers; ++l) {
+    const LayerW& lw = h->layers[l];
+    // ---- self-attention over all K+T tokens of the row
+    TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16, H, lw.w_qkv, H, lw.b_qkv, w.qkv, 3 * H, MA, 3 * H, H,
+                 EPI_BIAS_BF16, nullptr, 0, &err));
+    {
+      AttentionArgs a;
+      a.q = w.qkv; a.k = w.qkv + H; a.v = w.qkv + 2 * H; a.out = w.ctx;
+      a.ldq = a.ldk = a.ldv = 3 * H; a.ldo = H;
+      a.rows = static_cast<int>(rows); a.heads = c.heads; a.nq = n;
+      a.q_seg1 = K; a.q_seg2 = T; a.q_base1 = 0; a.q_base2 = MQ;
+      a.kv_seg1 = K; a.kv_seg2 = T; a.kv_base1 = 0; a.kv_base2 = MQ;
+      a.scale_log2 = scale_log2;
+      KernelScope ks(h, TDC_K_ATTENTION, s);
+      TDC_TRY(attention_launch(a, s, &err));
+    }
+    TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.ctx, H, lw.w_ao, H, lw.b_ao, w.pre, H, MA, H, H, EPI_BIAS_RESID_F32,
+                 w.h_f32, H, &err));
+    TDC_TRY(ln(lw.ln_a_g, lw.ln_a_b, 0, MA));
+
+    // ---- cross-attention: query tokens only
+    if (lw.cross_index >= 0) {
+      TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16, H, lw.w_cq, H, lw.b_cq, w.qc, H, MQ, H, H, EPI_BIAS_BF16,
+                   nullptr, 0, &err));
+      AttentionArgs a;
+      a.q = w.qc; a.out = w.ctx; a.ldq = H; a.ldo = H;
+      a.k = w.kv + static_cast<size_t>(lw.cross_index) * 2 * H;
+      a.v = a.k + H;
+      a.ldk = a.ldv = kvw;
+      a.rows = static_cast<int>(rows); a.heads = c.heads; a.nq = K;
+      a.q_seg1 = K; a.q_seg2 = 0;
+      a.kv_seg1 = L; a.kv_seg2 = 0;
+      a.kv_len = kv_len;
+      a.scale_log2 = scale_log2;
+      {
+        KernelScope ks(h, TDC_K_ATTENTION, s);
+        TDC_TRY(attention_launch(a, s, &err));
+      }
+      TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.ctx, H, lw.w_co, H, lw.b_co, w.pre, H, MQ, H, H, EPI_BIAS_RESID_F32,
+                   w.h_f32, H, &err));
+      TDC_TRY(ln(lw.ln_c_g, lw.ln_c_b, 0, MQ));
+    }
+
+    // ---- feed-forward: query tokens and text tokens use different weights
+    TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16, H, lw.w_fq1, H, lw.b_fq1, w.mid, I, MQ, I, H, EPI_BIAS_GELU_BF16,
+                 nullptr, 0, &err));
+    TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.mid, I, lw.w_fq2, I, lw.b_fq2, w.pre, H, MQ, H, I, EPI_BIAS_RESID_F32,
+                 w.h_f32, H, &err));
+    TDC_TRY(ln(lw.ln_fq_g, lw.ln_fq_b, 0, MQ));
+    if (T > 0) {
+      TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16 + MQ * H, H, lw.w_ft1, H, lw.b_ft1, w.mid, I, MT, I, H,
+                   EPI_BIAS_GELU_BF16, nullptr, 0, &err));
+      TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.mid, I, lw.w_ft2, I, lw.b_ft2, w.pre + MQ * H, H, MT, H, I,
+                   EPI_BIAS_RESID_F32, w.h_f32 + MQ * H, H, &err));
+      TDC_TRY(ln(lw.ln_ft_g, lw.ln_ft_b, MQ, MT));
+    }
+  }
+
+  if (!f.compress) {
+    const size_t osz = f.out_dtype == TDC_F32 ? 4 : 2;
+    void* out = static_cast<uint8_t*>(f.out) + static_cast<size_t>(row0) * n * H * osz;
+    KernelScope ks(h, TDC_K_ROWOPS, s);
+    TDC_TRY(gather_rows_launch(w.h_f32, H, static_cast<int>(rows), K, T, n, out, f.out_dtype, s, &err));
+  } else {
+    // vision_proj on the (contiguous) query slab, then unit-normalise every token
+    TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16, H, h->w_vp, H, h->b_vp, w.proj, c.d_out, MQ, c.d_out, H,
+                 EPI_BIAS_RESID_F32, nullptr, 0, &err));
+    const size_t osz = f.out_dtype == TDC_F32 ? 4 : 2;
+    void* out = static_cast<uint8_t*>(f.out) + static_cast<size_t>(row0) * K * c.d_out * osz;
+    KernelScope ks(h, TDC_K_ROWOPS, s);
+    TDC_TRY(l2_normalize_launch(w.proj, c.d_out, out, f.out_dtype, MQ, c.d_out, s, &err));
+  }
+  return TDC_OK;
+}
+
+int validate_call(tdc_handle* h, const ForwardCall& f) {
+  const tdc_config& c = h->cfg;
+  if (!h->loaded) return fail(h, TDC_ESTATE, "forward called before tdc_load_weights");
+  if (f.rows < 0 || f.L <= 0 || f.K <= 0 || f.T < 0) return fail(h, TDC_EINVAL, "rows/kv_tokens/num_query/num_text out of range");
+  if (f.rows > 0 && (f.query_embeds == nullptr || f.enc == nullptr || f.out == nullptr))
+    return fail(h, TDC_EINVAL, "null query_embeds / enc / out pointer");
+  if (f.T > 0) {
+    if (f.input_ids == nullptr) return fail(h, TDC_EINVAL, "num_text > 0 needs input_ids");
+    if (!h->have_text_ffn || !h->have_embeddings)
+      return fail(h, TDC_ESTATE, "text input needs the word/position embeddings and the text FFN weights");
+    if (f.T > c.max_pos) return fail(h, TDC_EINVAL, "num_text exceeds max_position_embeddings");
+  }
+  if (f.compress && !h->have_vp) return fail(h, TDC_ESTATE, "tdc_compress needs vision_proj weights (d_out > 0)");
+  for (int d : {f.query_dtype, f.enc_dtype, f.out_dtype})
+    if (d < TDC_BF16 || d > TDC_F32) return fail(h, TDC_EINVAL, "unknown dtype");
+  if (f.rows * static_cast<long long>(f.L) >= (1ll << 31))
+    return fail(h, TDC_EINVAL, "rows * kv_tokens must stay below 2^31 per call");
+  return TDC_OK;
+}
+
+int run_call(tdc_handle* h, const ForwardCall& f, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  const int rc = validate_call(h, f);
+  if (rc != TDC_OK) return rc;
+  if (f.rows == 0) return TDC_OK;
+  if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & (kAlign - 1)))
+    return fail(h, TDC_EINVAL, "workspace must be non-null and 256-byte aligned");
+  const bool conv = f.enc_dtype != TDC_BF16;
+  // largest row batch that fits the workspace (row cost is linear up to alignment padding)
+  const size_t one = carve_workspace(h, nullptr, 1, f.L, f.K, f.T, conv, f.compress).bytes;
+  const size_t all = carve_workspace(h, nullptr, f.rows, f.L, f.K, f.T, conv, f.compress).bytes;
+  long long batch = f.rows;
+  if (all > workspace_bytes) {
+    batch = static_cast<long long>(workspace_bytes / one);
+    while (batch > 0 && carve_workspace(h, nullptr, batch, f.L, f.K, f.T, conv, f.compress).bytes > workspace_bytes) --batch;
+    if (batch <= 0) return fail(h, TDC_EWORKSPACE, "workspace too small for a single row; see tdc_workspace_bytes");
+  }
+  for (long long r0 = 0; r0 < f.rows; r0 += batch) {
+    const int brc = forward_batch(h, f, r0, std::min(batch, f.rows - r0), static_cast<uint8_t*>(workspace), s);
+    if (brc != TDC_OK) return brc;
+  }
+  return TDC_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+int tdc_abi_version(void) { return TDC_B200_ABI_VERSION; }
+
+const char* tdc_last_error(const tdc_handle* h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
+
+int tdc_create(tdc_handle** out, const tdc_config* cfg) {
+  if (out == nullptr || cfg == nullptr) { g_create_error = "null argument"; return TDC_EINVAL; }
+  *out = nullptr;
+  const tdc_config& c = *cfg;
+  if (c.hidden <= 0 || c.heads <= 0 || c.hidden != c.heads * 64) { g_create_error = "hidden must equal heads * 64 (head size is fixed at 64)"; return TDC_EINVAL; }
+  if (c.hidden > 1024) { g_create_error = "hidden must be <= 1024"; return TDC_EINVAL; }
+  if (c.layers <= 0 || c.cross_freq <= 0 || c.intermediate <= 0 || c.intermediate % 8) { g_create_error = "bad layers / cross_freq / intermediate"; return TDC_EINVAL; }
+  if (c.d_enc <= 0 || c.d_enc % 8 || c.d_out < 0 || c.d_out % 8) { g_create_error = "d_enc and d_out must be multiples of 8"; return TDC_EINVAL; }
+  if (c.vocab < 0 || (c.vocab > 0 && c.max_pos <= 0)) { g_create_error = "bad vocab / max_pos"; return TDC_EINVAL; }
+  if (c.gemm_cta_group < 0 || c.gemm_cta_group > 2) { g_create_error = "gemm_cta_group must be 0, 1 or 2"; return TDC_EINVAL; }
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) { g_create_error = "no CUDA device: libtdc_b200 has no CPU fallback"; return TDC_ECUDA; }
+  int dev = 0, major = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) { g_create_error = "libtdc_b200 needs an sm_100 (Blackwell) device"; return TDC_ECUDA; }
+  tdc_handle* h = new tdc_handle();
+  h->cfg = c;
+  if (h->cfg.ln_eps <= 0.f) h->cfg.ln_eps = 1e-12f;
+  h->layers.resize(c.layers);
+  for (int l = 0; l < c.layers; ++l) if (l % c.cross_freq == 0) ++h->n_cross;
+  carve_weights(h, nullptr, &h->arena_bytes);
+  if (cudaMalloc(&h->arena, h->arena_bytes) != cudaSuccess) {
+    g_create_error = "cudaMalloc of the weight arena failed";
+    delete h;
+    return TDC_ENOMEM;
+  }
+  size_t dummy = 0;
+  carve_weights(h, static_cast<uint8_t*>(h->arena), &dummy);
+  *out = h;
+  return TDC_OK;
+}
+
+int tdc_destroy(tdc_handle* h) {
+  if (h == nullptr) return TDC_OK;
+  for (auto& pc : h->prof)
+    for (auto& e : pc.events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  if (h->arena) cudaFree(h->arena);
+  delete h;
+  return TDC_OK;
+}
+
+int tdc_load_weights(tdc_handle* h, const tdc_tensor* tensors, int32_t count, tdc_stream_t stream) {
+  if (h == nullptr) return TDC_EINVAL;
+  if (tensors == nullptr || count <= 0) return fail(h, TDC_EINVAL, "empty tensor table");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  std::vector<std::string> got;
+  for (int i = 0; i < count; ++i) {
+    const tdc_tensor& t = tensors[i];
+    if (t.name == nullptr || t.data == nullptr) return fail(h, TDC_EINVAL, "tensor with null name or data");
+    Slot slot;
+    std::string name = t.name;
+    if (!resolve_slot(h, name, &slot)) continue;  // tensors the path does not use (cls.*, position_ids, ...) are ignored
+    int64_t numel = 1;
+    for (int d = 0; d < t.ndim; ++d) numel *= t.shape[d];
+    const bool shape_ok = slot.cols == 0 ? (t.ndim == 1 && t.shape[0] == slot.rows)
+                                         : (t.ndim == 2 && t.shape[0] == slot.rows && t.shape[1] == slot.cols);
+    if (!shape_ok) return fail(h, TDC_EINVAL, "shape mismatch for tensor " + name);
+    const char* err = nullptr;
+    const int rc = convert_launch(t.data, t.dtype, slot.dst, slot.as_bf16 ? TDC_BF16 : TDC_F32, numel, s, &err);
+    if (rc != TDC_OK) return fail(h, rc, std::string("convert failed for ") + name + ": " + (err ? err : "?"));
+    ++h->launches;
+    got.push_back(name);
+  }
+  std::sort(got.begin(), got.end());
+  auto have_all = [&](int group, std::string* missing) {
+    for (const std::string& n : expected_names(h, group))
+      if (!std::binary_search(got.begin(), got.end(), n)) { if (missing) *missing = n; return false; }
+    return true;
+  };
+  std::string missing;
+  if (!have_all(0, &missing)) return fail(h, TDC_EINVAL, "missing tensor " + missing);
+  h->have_text_ffn = h->cfg.vocab > 0 && have_all(1, nullptr);
+  h->have_embeddings = h->cfg.vocab > 0 && have_all(2, nullptr);
+  h->have_vp = h->cfg.d_out > 0 && have_all(3, nullptr);
+  h->loaded = true;
+  return TDC_OK;
+}
+
+size_t tdc_workspace_bytes(const tdc_handle* h, int32_t rows, int32_t kv_len, int32_t num_query, int32_t num_text) {
+  if (h == nullptr || rows <= 0 || kv_len <= 0 || num_query <= 0 || num_text < 0) return 0;
+  // sized for the most demanding variant: non-bf16 encoder input + projection output
+  return carve_workspace(h, nullptr, rows, kv_len, num_query, num_text, true, h->cfg.d_out > 0).bytes;
+}
+
+int tdc_qformer_forward(tdc_handle* h, const void* query_embeds, int32_t query_dtype, const int32_t* query_set,
+                        const int64_t* input_ids, const int32_t* text_set, const void* enc, int32_t enc_dtype,
+                        const int32_t* kv_len, int32_t rows, int32_t kv_tokens, int32_t num_query, int32_t num_text,
+                        void* out_hidden, int32_t out_dtype, void* workspace, size_t workspace_bytes,
+                        tdc_stream_t stream) {
+  if (h == nullptr) return TDC_EINVAL;
+  ForwardCall f{query_embeds, query_dtype, query_set, input_ids, text_set, enc, enc_dtype, kv_len,
+                rows, kv_tokens, num_query, num_text, out_hidden, out_dtype, false};
+  return run_call(h, f, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int tdc_compress(tdc_handle* h, const void* query_embeds, int32_t query_dtype, const int32_t* query_set,
+                 const int64_t* input_ids, const int32_t* text_set, const void* enc, int32_t enc_dtype,
+                 const int32_t* kv_len, int32_t rows, int32_t kv_tokens, int32_t num_query, int32_t num_text,
+                 void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes, tdc_stream_t stream) {
+  if (h == nullptr) return TDC_EINVAL;
+  ForwardCall f{query_embeds, query_dtype, query_set, input_ids, text_set, enc, enc_dtype, kv_len,
+                rows, kv_tokens, num_query, num_text, out, out_dtype, true};
+  return run_call(h, f, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int tdc_proj_norm(tdc_handle* h, const void* hidden, int32_t hidden_dtype, int32_t rows, int32_t tokens_per_row,
+                  int32_t num_query, void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes,
+                  tdc_stream_t stream) {
+  if (h == nullptr) return TDC_EINVAL;
+  if (!h->loaded || !h->have_vp) return fail(h, TDC_ESTATE, "tdc_proj_norm needs loaded vision_proj weights");
+  if (rows < 0 || num_query <= 0 || tokens_per_row < num_query) return fail(h, TDC_EINVAL, "bad rows / tokens");
+  if (rows == 0) return TDC_OK;
+  if (hidden == nullptr || out == nullptr || workspace == nullptr) return fail(h, TDC_EINVAL, "null pointer");
+  const tdc_config& c = h->cfg;
+  const size_t M = static_cast<size_t>(rows) * num_query;
+  Carver cv{static_cast<uint8_t*>(workspace)};
+  __nv_bfloat16* x = cv.take<__nv_bfloat16>(M * c.hidden);
+  float* y = cv.take<float>(M * c.d_out);
+  if (cv.off > workspace_bytes) return fail(h, TDC_EWORKSPACE, "workspace too small for tdc_proj_norm");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const char* err = nullptr;
+  {
+    KernelScope ks(h, TDC_K_ROWOPS, s);
+    TDC_TRY(take_query_tokens_launch(hidden, hidden_dtype, rows, tokens_per_row, num_query, c.hidden, x, s, &err));
+  }
+  TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, x, c.hidden, h->w_vp, c.hidden, h->b_vp, y, c.d_out, M, c.d_out, c.hidden,
+               EPI_BIAS_RESID_F32, nullptr, 0, &err));
+  KernelScope ks(h, TDC_K_ROWOPS, s);
+  TDC_TRY(l2_normalize_launch(y, c.d_out, out, out_dtype, M, c.d_out, s, &err));
+  return TDC_OK;
+}
+
+int tdc_linear(const void* x, const void* w, const float* bias, void* y, int32_t m, int32_t n, int32_t k,
+               int32_t out_dtype, int32_t gelu, int32_t cta_group, tdc_stream_t stream) {
+  if (m == 0) return TDC_OK;
+  if (x == nullptr || w == nullptr || y == nullptr || m < 0) { g_create_error = "tdc_linear: null pointer"; return TDC_EINVAL; }
+  GemmProblem p;
+  p.a = x; p.lda = k; p.w = w; p.ldw = k; p.bias = bias; p.out = y; p.ldo = n; p.m = m; p.n = n; p.k = k;
+  if (out_dtype == TDC_F32) {
+    if (gelu) { g_create_error = "tdc_linear: gelu needs bf16 output"; return TDC_EINVAL; }
+    p.mode = EPI_BIAS_RESID_F32;
+  } else if (out_dtype == TDC_BF16) {
+    p.mode = gelu ? EPI_BIAS_GELU_BF16 : EPI_BIAS_BF16;
+  } else { g_create_error = "tdc_linear: out_dtype must be bf16 or fp32"; return TDC_EINVAL; }
+  p.cta_group = cta_group == 0 ? 2 : cta_group;
+  const char* err = nullptr;
+  const int rc = gemm_launch(p, static_cast<cudaStream_t>(stream), &err);
+  if (rc != TDC_OK) g_create_error = err ? err : "tdc_linear failed";
+  return rc;
+}
+
+int tdc_gelu_mlp(const void* x, const void* w0, const float* b0, const void* w1, const float* b1, void* mid, void* y,
+                 int32_t m, int32_t d_in, int32_t d_mid, int32_t d_out, tdc_stream_t stream) {
+  int rc = tdc_linear(x, w0, b0, mid, m, d_mid, d_in, TDC_BF16, 1, 0, stream);
+  if (rc != TDC_OK) return rc;
+  return tdc_linear(mid, w1, b1, y, m, d_out, d_mid, TDC_BF16, 0, 0, stream);
+}
+
+int tdc_avg_pool_tokens(const void* frames, int32_t dtype, int32_t n, int32_t tokens, int32_t d, int32_t num_query,
+                        void* out_bf16, tdc_stream_t stream) {
+  const char* err = nullptr;
+  const int rc = avg_pool_tokens_launch(frames, dtype, n, tokens, d, num_query, static_cast<__nv_bfloat16*>(out_bf16),
+                                        static_cast<cudaStream_t>(stream), &err);
+  if (rc != TDC_OK) g_create_error = err ? err : "tdc_avg_pool_tokens failed";
+  return rc;
+}
+
+int tdc_convert(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t count, tdc_stream_t stream) {
+  const char* err = nullptr;
+  const int rc = convert_launch(src, src_dtype, dst, dst_dtype, count, static_cast<cudaStream_t>(stream), &err);
+  if (rc != TDC_OK) g_create_error = err ? err : "tdc_convert failed";
+  return rc;
+}
+
+int tdc_set_profiling(tdc_handle* h, int32_t enabled) {
+  if (h == nullptr) return TDC_EINVAL;
+  h->profiling = enabled != 0;
+  return TDC_OK;
+}
+
+int tdc_reset_profile(tdc_handle* h) {
+  if (h == nullptr) return TDC_EINVAL;
+  for (auto& pc : h->prof) pc.used = 0;
+  return TDC_OK;
+}
+
+int tdc_get_profile(tdc_handle* h, int32_t kernel_class, double* total_ms, int64_t* launches) {
+  if (h == nullptr || kernel_class < 0 || kernel_class >= TDC_K_COUNT) return TDC_EINVAL;
+  ProfileClass& pc = h->prof[kernel_class];
+  double tot = 0;
+  for (size_t i = 0; i < pc.used; ++i) {
+    if (cudaEventSynchronize(pc.events[i].second) != cudaSuccess) return fail(h, TDC_ECUDA, "event synchronize failed");
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pc.events[i].first, pc.events[i].second) != cudaSuccess)
+      return fail(h, TDC_ECUDA, "event elapsed time failed");
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = static_cast<int64_t>(pc.used);
+  return TDC_OK;
+}
+
+int64_t tdc_launch_count(const tdc_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,40 @@
+// Host-side interface of the tcgen05 GEMM (implementation: gemm_sm100.cu).
+//
+//   C[M,N] = epilogue( A[M,K] . W[N,K]^T )        A, W bf16 row-major (K contiguous)
+//
+// which is exactly nn.Linear's layout (weight [out_features, in_features]), so
+// reference weights are used as stored, only cast to bf16.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tdc {
+
+enum GemmEpilogueMode : int {
+  EPI_BIAS_BF16 = 0,       // out bf16  = acc + bias
+  EPI_BIAS_GELU_BF16 = 1,  // out bf16  = gelu_erf(acc + bias)
+  EPI_BIAS_RESID_F32 = 2,  // out fp32  = acc + bias (+ resid fp32 if non-null)
+};
+
+struct GemmProblem {
+  const void* a = nullptr;  // bf16 [M, K], row pitch lda elements
+  const void* w = nullptr;  // bf16 [N, K], row pitch ldw elements
+  long long lda = 0, ldw = 0;
+  int m = 0, n = 0, k = 0;
+  void* out = nullptr;  // bf16 or fp32 [M, N], row pitch ldo elements
+  long long ldo = 0;
+  const float* bias = nullptr;   // [N] or null
+  const float* resid = nullptr;  // fp32 [M, N] pitch ldr, or null (mode 2 only)
+  long long ldr = 0;
+  int mode = EPI_BIAS_BF16;
+  int cta_group = 0;  // 0 = library default, 1 = single-CTA tiles, 2 = CTA-pair (cta_group::2) tiles
+};
+
+// Returns 0 on success, otherwise a negative tdc_status; on failure *err (if
+// non-null) points at a static description.
+int gemm_launch(const GemmProblem& p, cudaStream_t stream, const char** err);
+
+// Number of kernels gemm_launch enqueues (always 1) — kept for launch accounting.
+inline int gemm_launch_count() { return 1; }
+
+}  // namespace tdc

@@ -1,0 +1,80 @@
+// Launch interfaces of the non-GEMM kernels (attention.cu, rowops.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include "tdc_b200.h"
+
+namespace tdc {
+
+// Token addressing shared by the kernels: the Q-Former's sequence of one row is
+// [K query tokens | T text tokens] (tdc/Qformer.py:95-102).  The library stores the two
+// kinds in two contiguous slabs — all query tokens of all rows first, then all text
+// tokens — so that the query-only stages (cross-attention, query FFN; Qformer.py:430-454)
+// and the text-only FFN (:455-462) are plain dense GEMMs over contiguous rows.
+// Token i of row r lives at slab row
+//     i <  seg1 ?  base1 + r*seg1 + i  :  base2 + r*seg2 + (i - seg1).
+struct AttentionArgs {
+  const __nv_bfloat16* q = nullptr;  // head h of a token at q + row*ldq + h*64
+  const __nv_bfloat16* k = nullptr;
+  const __nv_bfloat16* v = nullptr;
+  __nv_bfloat16* out = nullptr;  // same token addressing as q
+  long long ldq = 0, ldk = 0, ldv = 0, ldo = 0;
+  int rows = 0, heads = 0;
+  int nq = 0;  // queries per row (= q_seg1 + q_seg2)
+  int q_seg1 = 0, q_seg2 = 0;
+  long long q_base1 = 0, q_base2 = 0;
+  int kv_seg1 = 0, kv_seg2 = 0;
+  long long kv_base1 = 0, kv_base2 = 0;
+  const int32_t* kv_len = nullptr;  // [rows] or null
+  float scale_log2 = 0.f;           // log2(e) / sqrt(head size)
+};
+int attention_launch(const AttentionArgs& a, cudaStream_t stream, const char** err);
+
+// y = LayerNorm(x) * gamma + beta, fp32 statistics (tdc/Qformer.py:285-289, 371-375).
+// x fp32 [rows, width]; writes y as fp32 (nullable) and bf16 (nullable).
+int layernorm_launch(const float* x, long long ldx, const float* gamma, const float* beta, float eps, float* y_f32,
+                     __nv_bfloat16* y_bf16, long long ldy, long long rows, int width, cudaStream_t stream,
+                     const char** err);
+
+// BertEmbeddings.forward (tdc/Qformer.py:78-108): query tokens = query_embeds (no position
+// embedding), text tokens = word_emb[id] + pos_emb[t]; LayerNorm over everything.
+struct EmbedArgs {
+  const void* query_embeds = nullptr;  // [n_sets, K, H]
+  int query_dtype = TDC_F32;
+  const int32_t* query_set = nullptr;  // [rows] or null
+  const int64_t* input_ids = nullptr;  // [n_text_sets, T] or null
+  const int32_t* text_set = nullptr;   // [rows] or null
+  const float* word_emb = nullptr;     // [vocab, H]
+  const float* pos_emb = nullptr;      // [max_pos, H]
+  int vocab = 0;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  float eps = 1e-12f;
+  float* h_f32 = nullptr;  // [rows*K + rows*T, H] slab layout
+  __nv_bfloat16* h_bf16 = nullptr;
+  int rows = 0, num_query = 0, num_text = 0, hidden = 0;
+};
+int embed_layernorm_launch(const EmbedArgs& a, cudaStream_t stream, const char** err);
+
+// out[r, i, :] = h[slab row of (r, i)] for i < tokens_out, converted to out_dtype.
+int gather_rows_launch(const float* h_f32, int hidden, int rows, int num_query, int num_text, int tokens_out,
+                       void* out, int out_dtype, cudaStream_t stream, const char** err);
+
+// F.normalize(x, dim=-1) (eps 1e-12; tdc/cambrian_arch.py:1664-1667): x fp32 [rows, width] -> out_dtype.
+int l2_normalize_launch(const float* x, long long ldx, void* out, int out_dtype, long long rows, int width,
+                        cudaStream_t stream, const char** err);
+
+// Elementwise dtype conversion.
+int convert_launch(const void* src, int src_dtype, void* dst, int dst_dtype, long long count, cudaStream_t stream,
+                   const char** err);
+
+// hidden [rows, tokens_per_row, H] (dtype) -> bf16 [rows*num_query, H] (first num_query tokens of every row)
+int take_query_tokens_launch(const void* hidden, int dtype, int rows, int tokens_per_row, int num_query, int width,
+                             __nv_bfloat16* out, cudaStream_t stream, const char** err);
+
+// adaptive_avg_pool1d over the token axis: bins [floor(i*L/K), ceil((i+1)*L/K)) (tdc/cambrian_arch.py:1633-1637)
+int avg_pool_tokens_launch(const void* frames, int dtype, int n, int tokens, int d, int num_query,
+                           __nv_bfloat16* out, cudaStream_t stream, const char** err);
+
+}  // namespace tdc
