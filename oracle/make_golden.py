@@ -1,0 +1,93 @@
+"""TEST INFRASTRUCTURE — generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):  python -m oracle.make_golden
+
+For every case the reference `BertModel` (tdc/Qformer.py, imported through oracle/ref_shim.py)
+is constructed, loaded with the seeded synthetic state dict of oracle/synth.py and called
+exactly like the TDC call site (tdc/cambrian_arch.py:1653-1667), in fp32 on the CPU.
+Only geometry + seeds + the reference outputs are stored; weights and inputs are regenerated
+from the seeds by the tests.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import ref_shim
+from oracle.synth import QFormerGeometry, make_inputs, make_state_dict
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+SMALL = QFormerGeometry(hidden=128, heads=2, intermediate=256, layers=4, cross_freq=2, d_enc=96, d_out=160,
+                        vocab=64, max_pos=32)
+FREQ1 = QFormerGeometry(hidden=64, heads=1, intermediate=128, layers=2, cross_freq=1, d_enc=40, d_out=72,
+                        vocab=32, max_pos=16)
+FULL_LITERAL = QFormerGeometry(d_enc=1152, d_out=3072)   # BASELINE config 1/2: SigLIP-width tokens, Llama-3.2-3B out
+FULL_QWEN = QFormerGeometry(d_enc=3584, d_out=3584)      # reference order, Qwen2-7B widths
+
+# name -> (geometry, seed, stress, rows, kv_tokens, K, T, audio_tokens, kv_len)
+CASES = {
+    "small_notext": (SMALL, 11, 0.0, 5, 23, 8, 0, 0, None),
+    "small_text": (SMALL, 12, 0.0, 3, 37, 8, 5, 7, None),
+    "small_stress_k16": (SMALL, 13, 8.0, 4, 50, 16, 3, 0, None),
+    "small_kvlen": (SMALL, 14, 8.0, 4, 40, 8, 0, 0, [40, 17, 1, 33]),
+    "small_k20_ragged_queries": (SMALL, 15, 0.0, 2, 19, 20, 4, 0, None),
+    "freq1_speech_style": (FREQ1, 16, 8.0, 3, 30, 1, 0, 0, None),  # audio_encoder.py-style: 1 query, cross every layer
+    "full_literal_l194": (FULL_LITERAL, 21, 0.0, 2, 194, 16, 0, 50, None),
+    "full_qwen_l206_text": (FULL_QWEN, 22, 2.0, 2, 206, 16, 6, 50, None),
+}
+
+
+def run_reference(geom, sd_np, inputs, num_query, kv_len=None):
+    model = ref_shim.build_reference_bert(geom, num_query)
+    own = model.state_dict()
+    load = {k: torch.from_numpy(v) for k, v in sd_np.items() if not k.startswith("vision_proj")}
+    missing = [k for k in own if k not in load and not k.endswith("position_ids")]
+    # text FFN / embeddings absent from a text-less state dict keep their (unused) init values
+    model.load_state_dict(load, strict=False)
+    assert all(("intermediate.dense" in k or "output.dense" in k or "output.LayerNorm" in k or "embeddings." in k)
+               for k in missing), missing
+    q = torch.from_numpy(inputs["query_embeds"])
+    enc = torch.from_numpy(inputs["enc"])
+    ids = torch.from_numpy(inputs["input_ids"]) if inputs["input_ids"] is not None else None
+    if kv_len is None:
+        atts = torch.ones(enc.shape[:-1], dtype=torch.long)   # cambrian_arch.py:1648-1650
+    else:
+        atts = (torch.arange(enc.shape[1])[None, :] < torch.tensor(kv_len)[:, None]).long()
+    with torch.no_grad():
+        out = model(input_ids=ids, query_embeds=q, encoder_hidden_states=enc, encoder_attention_mask=atts,
+                    use_cache=False, return_dict=True)
+        hidden = out.last_hidden_state
+        vp = torch.nn.Linear(geom.hidden, geom.d_out)
+        vp.weight.data = torch.from_numpy(sd_np["vision_proj.weight"])
+        vp.bias.data = torch.from_numpy(sd_np["vision_proj.bias"])
+        comp = F.normalize(vp(hidden[:, :num_query]), dim=-1)   # cambrian_arch.py:1664-1667
+    return hidden.numpy(), comp.numpy()
+
+
+def main(only=None):
+    assert ref_shim.reference_available(), "needs /root/reference"
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.manual_seed(0)
+    for name, (geom, seed, stress, rows, L, K, T, audio, kv_len) in CASES.items():
+        if only and name not in only:
+            continue
+        sd = make_state_dict(geom, seed, stress=stress, with_text=T > 0)
+        inputs = make_inputs(geom, seed, rows, L, K, T, audio_tokens=audio)
+        hidden, comp = run_reference(geom, sd, inputs, K, kv_len)
+        meta = dict(geometry=geom.to_dict(), seed=seed, stress=stress, rows=rows, kv_tokens=L, num_query=K,
+                    num_text=T, audio_tokens=audio, kv_len=kv_len,
+                    generator="oracle/make_golden.py on reference tdc/Qformer.py (fp32 CPU)",
+                    torch=torch.__version__)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"qformer_{name}.npz"), meta=json.dumps(meta),
+                            hidden=hidden.astype(np.float32), compressed=comp.astype(np.float32))
+        print(f"{name}: hidden {hidden.shape} compressed {comp.shape}")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

@@ -1,0 +1,225 @@
+"""The TDC driver: everything `prepare_inputs_labels_for_multimodal` does between "frames of one
+video are projected" and "compressed token sequence is spliced into the prompt"
+(tdc/cambrian_arch.py:1507-1709), batched over ALL chunks of the video instead of the
+reference's Python double loop with <= 7 rows per Q-Former call.
+
+`TDCCompressor` owns the same attributes the reference keeps on the model
+(cambrian_arch.py:148-150, 180-181, 469-484): `Qformer`, `query_tokens`, `vision_proj`,
+`query_proj`, `frame_seg`, optional `audio_proj` — same names, same shapes, so the matching
+entries of a reference checkpoint (`model.<name>`) load unchanged.
+
+Data flow per video (n_frames frames already split into DINO segments):
+  host ints : segments -> chunks of <= 8 frames -> static frame + dynamic rows  (plan_chunks)
+  GPU       : audio_proj GEMM  ->  KV tokens [R, Lv(+La), d]
+              avg-pool(static) -> query_proj GEMM -> one query set per chunk    (Avg_pool)
+              libtdc tdc_compress: Q-Former + vision_proj + L2-normalise for all R rows
+              scatter static / compressed / frame_seg tokens to their final offsets
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+from torch import nn
+
+from .engine import avg_pool_tokens, linear
+from .qformer import QFormerConfig, TDCQFormer
+
+CHUNK_FRAMES = 8  # cambrian_arch.py:1606
+
+
+@dataclass
+class ChunkPlan:
+    """Host-side index plan of one video (pure integers, no device work)."""
+    static_frames: np.ndarray   # [C]   frame index of every chunk's key frame
+    chunk_len: np.ndarray       # [C]   frames in the chunk (1..8)
+    row_frames: np.ndarray      # [R]   frame index of every Q-Former row
+    row_chunk: np.ndarray       # [R]   chunk index of every row
+    rows_per_chunk: np.ndarray  # [C]
+
+    @property
+    def num_chunks(self) -> int:
+        return int(self.static_frames.shape[0])
+
+    @property
+    def num_rows(self) -> int:
+        return int(self.row_frames.shape[0])
+
+
+def plan_chunks(segment_sizes: Sequence[int], keep_static: bool = True) -> ChunkPlan:
+    """segments -> chunks of <= 8 frames (cambrian_arch.py:1603-1628).  With `keep_static` the
+    chunk's first frame passes through uncompressed and the others become rows; without it
+    every frame of the chunk is a row (and the first frame still provides the queries)."""
+    static, clen, rf, rc, rpc = [], [], [], [], []
+    base = 0
+    for n in segment_sizes:
+        n = int(n)
+        for start in range(0, n, CHUNK_FRAMES):
+            ln = min(CHUNK_FRAMES, n - start)
+            c = len(static)
+            static.append(base + start)
+            clen.append(ln)
+            frames = range(base + start + 1, base + start + ln) if keep_static else range(base + start,
+                                                                                          base + start + ln)
+            rf.extend(frames)
+            rc.extend([c] * len(frames))
+            rpc.append(len(frames))
+        base += n
+    i64 = np.int64
+    return ChunkPlan(np.asarray(static, i64), np.asarray(clen, i64), np.asarray(rf, i64), np.asarray(rc, i64),
+                     np.asarray(rpc, i64))
+
+
+def output_layout(plan: ChunkPlan, static_tokens: int, num_query: int, keep_static: bool = True, add_sep: bool = True):
+    """Token offsets of the assembled sequence (cambrian_arch.py:1617-1623, 1668-1692).
+    Returns (chunk_offset [C], chunk_tokens [C], row_offset [R])."""
+    sep = 1 if add_sep else 0
+    head = (static_tokens + sep) if keep_static else 0
+    chunk_tokens = head + plan.rows_per_chunk * (num_query + sep)
+    chunk_offset = np.concatenate([[0], np.cumsum(chunk_tokens)[:-1]]) if plan.num_chunks else np.zeros(0, np.int64)
+    first_row = np.concatenate([[0], np.cumsum(plan.rows_per_chunk)[:-1]]) if plan.num_chunks else np.zeros(0, np.int64)
+    within = np.arange(plan.num_rows) - first_row[plan.row_chunk] if plan.num_rows else np.zeros(0, np.int64)
+    row_offset = chunk_offset[plan.row_chunk] + head + within * (num_query + sep) if plan.num_rows else np.zeros(0, np.int64)
+    return chunk_offset.astype(np.int64), chunk_tokens.astype(np.int64), row_offset.astype(np.int64)
+
+
+def truncation_keep_index(chunk_offset: np.ndarray, chunk_tokens: np.ndarray, max_visual_len: int) -> Optional[np.ndarray]:
+    """Budget truncation (cambrian_arch.py:1694-1709): when over budget drop the last
+    ceil(excess / num_chunks) tokens of EVERY chunk, then hard-clip.  Returns the kept token
+    indices, or None when nothing is dropped."""
+    total = int(chunk_tokens.sum())
+    if max_visual_len is None or total <= max_visual_len:
+        return None
+    force_remove = math.ceil((total - max_visual_len) / len(chunk_tokens))
+    keep = []
+    for off, n in zip(chunk_offset.tolist(), chunk_tokens.tolist()):
+        kept = max(n - force_remove, 0) if force_remove > 0 else n   # x[:-k] semantics
+        keep.append(np.arange(off, off + kept, dtype=np.int64))
+    idx = np.concatenate(keep) if keep else np.zeros(0, np.int64)
+    return idx[:max_visual_len]
+
+
+class TDCCompressor(nn.Module):
+    """`initialize_compressor` (cambrian_arch.py:469-484) + the TDC block (:1507-1709)."""
+
+    def __init__(self, llm_hidden_size: int, context_token_num: int = 16, query_type: str = "Avg_pool",
+                 text_input: bool = True, add_static: bool = True, audio_input: bool = False,
+                 qformer_config: Optional[QFormerConfig] = None, with_lm_head: bool = False):
+        super().__init__()
+        if query_type not in ("Avg_pool", "learned"):
+            raise ValueError("query_type must be 'Avg_pool' or 'learned' (cambrian_arch.py:1633-1640)")
+        cfg = qformer_config or QFormerConfig()
+        cfg.encoder_width = llm_hidden_size          # encoder_width = config.hidden_size (:470, :408)
+        cfg.query_length = context_token_num
+        self.llm_hidden_size = llm_hidden_size
+        self.context_token_num = context_token_num
+        self.query_type = query_type
+        self.text_input = text_input
+        self.add_static = add_static
+        self.Qformer = TDCQFormer(cfg, with_lm_head=with_lm_head)
+        self.query_tokens = nn.Parameter(torch.zeros(1, context_token_num, cfg.hidden_size))
+        self.query_tokens.data.normal_(mean=0.0, std=cfg.initializer_range)
+        self.vision_proj = nn.Linear(cfg.hidden_size, llm_hidden_size)
+        self.query_proj = nn.Linear(llm_hidden_size, cfg.hidden_size)
+        self.frame_seg = nn.Parameter(torch.randn(llm_hidden_size))
+        if audio_input:
+            self.audio_proj = nn.Linear(768, llm_hidden_size)
+        self.eval()
+
+    # ------------------------------------------------------------------------------------
+    def _engine(self):
+        extra = {"vision_proj.weight": self.vision_proj.weight, "vision_proj.bias": self.vision_proj.bias}
+        key = (self.vision_proj.weight.data_ptr(), self.vision_proj.weight._version, self.vision_proj.bias._version)
+        return self.Qformer.bert.engine(d_out=self.llm_hidden_size, extra_state=extra, extra_key=key)
+
+    def build_queries(self, static_visual: torch.Tensor):
+        """[C, Lv, d] visual-only key frames -> query sets [C, K, hidden] fp32 (cambrian_arch.py:1629-1640).
+        The key frame is taken BEFORE the audio tokens are appended (:1609 vs :1614)."""
+        if self.query_type == "learned":
+            return self.query_tokens.detach().float(), True
+        pooled = avg_pool_tokens(static_visual, self.context_token_num)            # [C, K, d] bf16
+        q = linear(pooled, self.query_proj.weight, self.query_proj.bias, out_dtype=torch.float32)
+        return q, False
+
+    @torch.no_grad()
+    def compress_video(self, visual_emb_frame: torch.Tensor, segment_sizes: Sequence[int],
+                       input_ids: Optional[torch.Tensor] = None, audio_frames: Optional[torch.Tensor] = None,
+                       max_visual_len: Optional[int] = None, return_parts: bool = False):
+        """visual_emb_frame [n_frames, Lv, d] (one video), segment_sizes (frames per DINO segment),
+        input_ids [1, T] BERT ids of the prompt (used iff text_input), audio_frames [n_frames, La, 768]
+        per-frame BEATs tokens (iff the video has audio).  Returns the token sequence
+        `new_visual_emb_frames[:max_visual_len]` of cambrian_arch.py:1694-1709."""
+        if self.training:
+            raise RuntimeError("TDCCompressor is inference-only (eval mode)")
+        if not visual_emb_frame.is_cuda:
+            raise RuntimeError("TDCCompressor needs CUDA tensors: there is no CPU fallback")
+        n_frames, Lv, d = visual_emb_frame.shape
+        if sum(int(s) for s in segment_sizes) != n_frames:
+            raise ValueError("segment_sizes must sum to the number of frames")
+        dev, dtype = visual_emb_frame.device, visual_emb_frame.dtype
+        K = self.context_token_num
+        plan = plan_chunks(segment_sizes, self.add_static)
+        C_, R = plan.num_chunks, plan.num_rows
+        static_idx = torch.from_numpy(plan.static_frames).to(dev)
+        row_idx = torch.from_numpy(plan.row_frames).to(dev)
+
+        # --- KV tokens of every row: the frame's visual tokens (+ projected audio tokens, :1611-1614)
+        La = 0
+        audio_tok = None
+        if audio_frames is not None:
+            if not hasattr(self, "audio_proj"):
+                raise RuntimeError("audio_frames given but the compressor was built with audio_input=False")
+            La = audio_frames.shape[1]
+            audio_tok = linear(audio_frames.to(dev), self.audio_proj.weight, self.audio_proj.bias,
+                               out_dtype=torch.bfloat16).to(dtype)                 # [n_frames, La, d]
+        L = Lv + La
+        if La:
+            enc = torch.empty((R, L, d), dtype=dtype, device=dev)
+            torch.index_select(visual_emb_frame, 0, row_idx, out=enc[:, :Lv]) if False else enc[:, :Lv].copy_(
+                visual_emb_frame.index_select(0, row_idx))
+            enc[:, Lv:].copy_(audio_tok.index_select(0, row_idx))
+            static_tok = torch.cat([visual_emb_frame.index_select(0, static_idx),
+                                    audio_tok.index_select(0, static_idx)], dim=1)  # [C, L, d]
+        else:
+            enc = visual_emb_frame.index_select(0, row_idx)
+            static_tok = visual_emb_frame.index_select(0, static_idx)
+        static_visual = static_tok[:, :Lv] if La else static_tok
+
+        # --- queries (one set per chunk) and prompt ids (one set per video)
+        comp = None
+        if R > 0:
+            q_sets, shared = self.build_queries(static_visual.contiguous())
+            query_set = torch.zeros(R, dtype=torch.int32) if shared else torch.from_numpy(plan.row_chunk.astype(np.int32))
+            ids = text_set = None
+            if self.text_input and input_ids is not None and input_ids.numel() > 0:
+                ids = input_ids.reshape(1, -1)
+                text_set = torch.zeros(R, dtype=torch.int32)
+            comp = self._engine().compress(q_sets, enc, ids, query_set=query_set, text_set=text_set, out_dtype=dtype)
+
+        # --- assemble [static, sep, (K compressed, sep) x rows] per chunk (:1668-1692)
+        Ls = L
+        chunk_off, chunk_tok, row_off = output_layout(plan, Ls, K, self.add_static, add_sep=True)
+        total = int(chunk_tok.sum())
+        out = torch.empty((total, d), dtype=dtype, device=dev)
+        seg = self.frame_seg.detach().to(dtype)
+        sep_pos = []
+        if self.add_static and C_ > 0:
+            idx = (chunk_off[:, None] + np.arange(Ls)[None, :]).reshape(-1)
+            out.index_copy_(0, torch.from_numpy(idx).to(dev), static_tok.reshape(-1, d))
+            sep_pos.append(chunk_off + Ls)
+        if R > 0:
+            idx = (row_off[:, None] + np.arange(K)[None, :]).reshape(-1)
+            out.index_copy_(0, torch.from_numpy(idx).to(dev), comp.reshape(-1, d))
+            sep_pos.append(row_off + K)
+        if sep_pos:
+            sp = torch.from_numpy(np.concatenate(sep_pos)).to(dev)
+            out.index_copy_(0, sp, seg[None, :].expand(sp.numel(), d).contiguous())
+        keep = truncation_keep_index(chunk_off, chunk_tok, max_visual_len)
+        if keep is not None:
+            out = out.index_select(0, torch.from_numpy(keep).to(dev))
+        if return_parts:
+            return out, comp, plan
+        return out

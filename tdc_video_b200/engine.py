@@ -1,0 +1,213 @@
+"""Handle-level wrapper: torch tensors in, libtdc_b200.so calls out.
+
+torch is used for device memory, streams and dtype bookkeeping only; every FLOP on this path
+happens in the library's sm_100a kernels.  No CPU fallback: constructing an engine without a
+CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional
+
+import torch
+
+from . import _lib
+from ._lib import TdcConfig, TdcTensor, check
+
+_DTYPES = {torch.bfloat16: _lib.TDC_BF16, torch.float16: _lib.TDC_F16, torch.float32: _lib.TDC_F32}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}; use bfloat16, float16 or float32") from None
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class QFormerEngine:
+    """Owns one `tdc_handle` (re-packed bf16 weights on one GPU) and a growable workspace."""
+
+    def __init__(self, *, hidden=768, heads=12, intermediate=3072, layers=12, cross_freq=2, d_enc=3584, d_out=0,
+                 vocab=0, max_pos=512, ln_eps=1e-12, device=None, gemm_cta_group=0,
+                 max_workspace_bytes: int = 24 << 30):
+        if not torch.cuda.is_available():
+            raise RuntimeError("tdc_video_b200 needs a CUDA (sm_100a) device: there is no CPU fallback")
+        self.lib = _lib.load_library()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.cfg = TdcConfig(hidden, heads, intermediate, layers, cross_freq, d_enc, d_out, vocab, max_pos,
+                             float(ln_eps), gemm_cta_group)
+        self.geometry = dict(hidden=hidden, heads=heads, intermediate=intermediate, layers=layers,
+                             cross_freq=cross_freq, d_enc=d_enc, d_out=d_out, vocab=vocab, max_pos=max_pos,
+                             ln_eps=ln_eps)
+        self.max_workspace_bytes = int(max_workspace_bytes)
+        self._ws: Optional[torch.Tensor] = None
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.tdc_create(C.byref(self._h), C.byref(self.cfg)), None, "tdc_create")
+
+    # -- lifecycle ------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.tdc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_weights(self, state: Mapping[str, "torch.Tensor"]) -> None:
+        """`state`: reference key names relative to `Qformer.bert.` plus `vision_proj.*`
+        (tensors or numpy arrays, any of fp32/fp16/bf16; copied to the device if needed)."""
+        keep, table = [], []
+        for name, value in state.items():
+            t = value if isinstance(value, torch.Tensor) else torch.as_tensor(value)
+            if not t.dtype.is_floating_point or t.dim() not in (1, 2):
+                continue  # e.g. embeddings.position_ids
+            t = t.detach().to(self.device).contiguous()
+            if t.dtype not in _DTYPES:
+                t = t.float()
+            keep.append(t)
+            shape = (C.c_int64 * 4)(*(list(t.shape) + [0] * (4 - t.dim())))
+            table.append(TdcTensor(name.encode(), t.data_ptr(), _dt(t), t.dim(), shape))
+        arr = (TdcTensor * len(table))(*table)
+        with torch.cuda.device(self.device):
+            check(self.lib.tdc_load_weights(self._h, arr, len(table), _stream(self.device)), self._h,
+                  "tdc_load_weights")
+            torch.cuda.current_stream(self.device).synchronize()  # sources may be freed after return
+
+    # -- workspace ------------------------------------------------------------------------
+    def workspace_bytes(self, rows: int, kv_tokens: int, num_query: int, num_text: int) -> int:
+        return int(self.lib.tdc_workspace_bytes(self._h, rows, kv_tokens, num_query, num_text))
+
+    def _workspace(self, rows, kv_tokens, num_query, num_text) -> torch.Tensor:
+        need = self.workspace_bytes(rows, kv_tokens, num_query, num_text)
+        floor = self.workspace_bytes(1, kv_tokens, num_query, num_text)
+        want = max(min(need, self.max_workspace_bytes), floor)
+        if self._ws is None or self._ws.numel() < want:
+            self._ws = None
+            self._ws = torch.empty(want, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # -- the hot path ---------------------------------------------------------------------
+    def _run(self, fn, what, query_embeds, enc, input_ids, query_set, text_set, kv_len, out_width, out_tokens,
+             out_dtype):
+        if enc.dim() != 3 or query_embeds.dim() != 3:
+            raise ValueError("query_embeds must be [sets, K, hidden] and enc [rows, L, d_enc]")
+        rows, L, d_enc = enc.shape
+        K = query_embeds.shape[1]
+        if d_enc != self.cfg.d_enc or query_embeds.shape[2] != self.cfg.hidden:
+            raise ValueError(f"width mismatch: enc {d_enc} vs d_enc {self.cfg.d_enc}, "
+                             f"query_embeds {query_embeds.shape[2]} vs hidden {self.cfg.hidden}")
+        T = 0 if input_ids is None else int(input_ids.shape[1])
+        if query_set is None and query_embeds.shape[0] != rows:
+            raise ValueError("query_embeds needs one query set per row unless query_set is given")
+        if T > 0 and text_set is None and input_ids.shape[0] != rows:
+            raise ValueError("input_ids needs one row per enc row unless text_set is given")
+        dev = self.device
+        enc = enc.to(dev).contiguous()
+        query_embeds = query_embeds.to(dev).contiguous()
+        ids = None if T == 0 else input_ids.to(dev, torch.int64).contiguous()
+        qs = None if query_set is None else query_set.to(dev, torch.int32).contiguous()
+        ts = None if text_set is None else text_set.to(dev, torch.int32).contiguous()
+        kl = None if kv_len is None else kv_len.to(dev, torch.int32).contiguous()
+        out_dtype = out_dtype or enc.dtype
+        out = torch.empty((rows, out_tokens(K, T), out_width), dtype=out_dtype, device=dev)
+        if rows == 0:
+            return out
+        ws = self._workspace(rows, L, K, T)
+        with torch.cuda.device(dev):
+            rc = fn(self._h, _ptr(query_embeds), _dt(query_embeds), _ptr(qs), _ptr(ids), _ptr(ts), _ptr(enc), _dt(enc),
+                    _ptr(kl), rows, L, K, T, _ptr(out), _dt(out), _ptr(ws), ws.numel(), _stream(dev))
+        check(rc, self._h, what)
+        return out
+
+    def forward(self, query_embeds, enc, input_ids=None, *, query_set=None, text_set=None, kv_len=None,
+                out_dtype=None) -> torch.Tensor:
+        """last_hidden_state [rows, K+T, hidden] (tdc_qformer_forward)."""
+        return self._run(self.lib.tdc_qformer_forward, "tdc_qformer_forward", query_embeds, enc, input_ids, query_set,
+                         text_set, kv_len, self.cfg.hidden, lambda K, T: K + T, out_dtype)
+
+    def compress(self, query_embeds, enc, input_ids=None, *, query_set=None, text_set=None, kv_len=None,
+                 out_dtype=None) -> torch.Tensor:
+        """normalize(vision_proj(last_hidden_state[:, :K])) [rows, K, d_out] (tdc_compress)."""
+        if self.cfg.d_out <= 0:
+            raise RuntimeError("engine was created without d_out: no vision_proj")
+        return self._run(self.lib.tdc_compress, "tdc_compress", query_embeds, enc, input_ids, query_set, text_set,
+                         kv_len, self.cfg.d_out, lambda K, T: K, out_dtype)
+
+    def proj_norm(self, hidden: torch.Tensor, num_query: int, out_dtype=None) -> torch.Tensor:
+        rows, tokens, H = hidden.shape
+        hidden = hidden.to(self.device).contiguous()
+        out = torch.empty((rows, num_query, self.cfg.d_out), dtype=out_dtype or hidden.dtype, device=self.device)
+        if rows == 0:
+            return out
+        need = rows * num_query * (H * 2 + self.cfg.d_out * 4) + 1024
+        ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.tdc_proj_norm(self._h, _ptr(hidden), _dt(hidden), rows, tokens, num_query, _ptr(out),
+                                        _dt(out), _ptr(ws), ws.numel(), _stream(self.device))
+        check(rc, self._h, "tdc_proj_norm")
+        return out
+
+    # -- instrumentation ------------------------------------------------------------------
+    def set_profiling(self, enabled: bool) -> None:
+        check(self.lib.tdc_set_profiling(self._h, int(enabled)), self._h)
+
+    def reset_profile(self) -> None:
+        check(self.lib.tdc_reset_profile(self._h), self._h)
+
+    def profile(self) -> Dict[str, Dict[str, float]]:
+        out = {}
+        for cls, name in enumerate(_lib.KERNEL_CLASS_NAMES):
+            ms, n = C.c_double(), C.c_int64()
+            check(self.lib.tdc_get_profile(self._h, cls, C.byref(ms), C.byref(n)), self._h)
+            out[name] = {"ms": ms.value, "launches": int(n.value)}
+        return out
+
+    def launch_count(self) -> int:
+        return int(self.lib.tdc_launch_count(self._h))
+
+
+# ---- free functions (no handle) -----------------------------------------------------------
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, gelu=False,
+           out_dtype=torch.bfloat16, cta_group=0) -> torch.Tensor:
+    """y = x . weight^T + bias on the tcgen05 GEMM (tdc_linear).  x [..., k], weight [n, k]."""
+    lib = _lib.load_library()
+    if not x.is_cuda:
+        raise RuntimeError("tdc_video_b200.linear needs CUDA tensors: there is no CPU fallback")
+    k = x.shape[-1]
+    n = weight.shape[0]
+    x2 = x.reshape(-1, k).to(torch.bfloat16).contiguous()
+    w = weight.to(x.device, torch.bfloat16).contiguous()
+    b = None if bias is None else bias.to(x.device, torch.float32).contiguous()
+    y = torch.empty((x2.shape[0], n), dtype=out_dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.tdc_linear(_ptr(x2), _ptr(w), _ptr(b), _ptr(y), x2.shape[0], n, k, _DTYPES[out_dtype], int(gelu),
+                            cta_group, _stream(x.device))
+    check(rc, None, "tdc_linear")
+    return y.reshape(*x.shape[:-1], n)
+
+
+def avg_pool_tokens(frames: torch.Tensor, num_query: int) -> torch.Tensor:
+    """[n, tokens, d] -> [n, K, d] bf16, adaptive average pooling over tokens (tdc_avg_pool_tokens)."""
+    lib = _lib.load_library()
+    if not frames.is_cuda:
+        raise RuntimeError("tdc_video_b200.avg_pool_tokens needs CUDA tensors: there is no CPU fallback")
+    frames = frames.contiguous()
+    n, tokens, d = frames.shape
+    out = torch.empty((n, num_query, d), dtype=torch.bfloat16, device=frames.device)
+    with torch.cuda.device(frames.device):
+        rc = lib.tdc_avg_pool_tokens(_ptr(frames), _dt(frames), n, tokens, d, num_query, _ptr(out),
+                                     _stream(frames.device))
+    check(rc, None, "tdc_avg_pool_tokens")
+    return out
