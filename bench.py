@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — TDC compression throughput (video-seconds/s) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload hour_qwen7b|cfg2_llama3b]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference algorithm on the host CPU cores
+
+One "step" = one pass of the hot path over one synthetic video per GPU: for every dynamic
+frame (row) the Q-Former (12 layers, cross-attention to the frame's L KV tokens) + vision_proj
++ L2-normalise, i.e. tdc/cambrian_arch.py:1603-1692 for all chunks at once, then (N > 1) an
+NCCL all-gather of the compressed tokens so that every rank holds the ordered sequence.
+
+ * `value`  : whole-job video-seconds/s, inputs resident in HBM, CUDA-event timed, max over ranks
+ * `e2e`    : the same through `QFormerEngine.compress_host` with the KV tokens in pinned HOST
+              memory (H2D of every row inside the timed region, result copied back to host)
+ * `roofline`: dominant kernel = the cross-attention K/V projection GEMM (tcgen05), algorithmic
+              FLOPs / its CUDA-event time (events on the launching stream, recorded by the library)
+ * `cpu_baseline`: the reference algorithm (oracle port, fp32 torch) on the host cores, bounded sample
+
+Synthetic data, random-init weights (oracle/synth.py statistics); weak scaling: every GPU
+compresses its own `segments` video-seconds.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json config 3 / north_star target: 1-hour video, TDC-Qwen2-7B shapes, reference order
+    # (frame tokens already in LLM width): 3600 one-second segments x 4 frames, frame 0 static ->
+    # 3 rows per segment; row KV = 144 visual + 12 newline + 50 audio tokens.
+    "hour_qwen7b": dict(segments=3600, frames_per_segment=4, kv_tokens=206, audio_tokens=50, d_enc=3584, d_out=3584,
+                        num_query=16, num_text=0, label="1-hour video, Qwen2-7B widths (d=3584), L=206, K=16"),
+    # BASELINE.json config 2: 256 segments, Llama-3.2-3B widths
+    "cfg2_llama3b": dict(segments=256, frames_per_segment=4, kv_tokens=206, audio_tokens=50, d_enc=3072, d_out=3072,
+                         num_query=16, num_text=0, label="256-segment video, Llama-3.2-3B widths (d=3072), L=206, K=16"),
+}
+H, I, LAYERS, HEADS, N_CROSS = 768, 3072, 12, 12, 6
+
+
+def flops_per_row(L, d_enc, K, T, d_out):
+    """Algorithmic FLOPs of one row, reference formulation."""
+    n = K + T
+    kv = N_CROSS * 2 * (2 * L * d_enc * H)
+    rest = (LAYERS * (8 * n * H * H + 4 * n * n * H) + N_CROSS * (4 * K * H * H + 4 * K * L * H)
+            + LAYERS * 4 * K * H * I + LAYERS * 4 * T * H * I + 2 * K * H * d_out)
+    return kv + rest, kv
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops_sustained=d["bf16_tflops_sustained"], tflops_burst=d["bf16_tflops"], hbm=d["hbm_gbs"],
+                    source="MEASURED_PEAKS.json")
+    return dict(tflops_sustained=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # samples under load = upper half of the clock samples (idle samples bracket the region)
+        load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_problem(w, seed):
+    """Synthetic video of the workload: per-row KV tokens, one query set per segment (Avg_pool-style:
+    all rows of a segment share the queries derived from its static frame)."""
+    from oracle.synth import QFormerGeometry, make_state_dict
+    geom = QFormerGeometry(d_enc=w["d_enc"], d_out=w["d_out"], vocab=0)
+    sd = make_state_dict(geom, seed, with_text=False)
+    rows = w["segments"] * (w["frames_per_segment"] - 1)
+    return geom, sd, rows
+
+
+def cpu_baseline(geom, sd, w, sample_rows, seed):
+    """The reference algorithm (oracle port of tdc/Qformer.py + vision_proj + normalize), fp32 torch on
+    all host cores, batched as ONE call (kinder to the CPU than the reference's <= 7-row loop)."""
+    from oracle import qformer_oracle as oracle
+    from oracle.synth import make_inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inp = make_inputs(geom, seed, sample_rows, w["kv_tokens"], w["num_query"], 0, audio_tokens=w["audio_tokens"])
+    sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
+    with torch.no_grad():
+        oracle.compress(sd_t, geom, inp["query_embeds"][:2], inp["enc"][:2])  # warm-up
+        t0 = time.perf_counter()
+        oracle.compress(sd_t, geom, inp["query_embeds"], inp["enc"])
+        dt = time.perf_counter() - t0
+    rows_per_s = sample_rows / dt
+    return rows_per_s / (w["frames_per_segment"] - 1), dt, cores
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    geom, sd, rows = build_problem(w, 1234)
+    sample = args.cpu_sample_rows
+    vals, dts = [], []
+    for i in range(args.warmup + args.steps):
+        v, dt, cores = cpu_baseline(geom, sd, w, sample, 4321 + i)
+        if i >= args.warmup:
+            vals.append(v); dts.append(dt)
+    value = statistics.mean(vals)
+    line = {
+        "impl": "reference", "metric": "video_seconds_per_sec", "value": value, "unit": "video-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(dts),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["label"], "rows_per_step_sample": sample},
+        "cpu_baseline": {"value": value, "unit": "video-s/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} rows (= {sample / (w['frames_per_segment'] - 1):.1f} video-s) of the "
+                                   f"workload per step, oracle port of the reference (fp32 torch, one batch)"},
+        "e2e": {"value": value, "unit": "video-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="hour_qwen7b", choices=sorted(WORKLOADS))
+    ap.add_argument("--segments", type=int, default=0, help="override segments per GPU")
+    ap.add_argument("--cpu-sample-rows", type=int, default=48)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-rows-per-batch", type=int, default=1200)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cta-group", type=int, default=0)
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.segments:
+        w["segments"] = args.segments
+    if args.impl == "reference":
+        return run_reference_arm(args, w)
+
+    import torch.distributed as dist
+    from tdc_video_b200 import QFormerEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    geom, sd, rows = build_problem(w, 1234)
+    L, K, d_enc, d_out = w["kv_tokens"], w["num_query"], w["d_enc"], w["d_out"]
+    S = w["segments"]
+    eng = QFormerEngine(d_enc=d_enc, d_out=d_out, vocab=0, device=dev, gemm_cta_group=args.cta_group)
+    eng.load_weights(sd)
+
+    # ---- synthetic inputs, generated on the host in pinned memory (also the e2e source), then made resident
+    # (values are drawn with the device RNG for speed — 8e9 normals — then the HOST copy is the
+    #  source of truth: the resident tensor is uploaded from it, and e2e streams it every step)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    enc_host = torch.empty((rows, L, d_enc), dtype=torch.bfloat16, pin_memory=not args.no_e2e)
+    chunk = 1024
+    for r0 in range(0, rows, chunk):
+        r1 = min(rows, r0 + chunk)
+        blk = torch.randn((r1 - r0, L, d_enc), generator=g, device=dev)
+        blk[:, L - w["audio_tokens"]:] *= 0.5
+        enc_host[r0:r1].copy_(blk.to(torch.bfloat16))
+    del blk
+    q_sets = torch.randn((S, K, H), generator=g, device=dev).cpu()    # one query set per segment
+    query_set = (torch.arange(rows) // (w["frames_per_segment"] - 1)).to(torch.int32)
+    enc = enc_host.to(dev)
+    q_dev, qs_dev = q_sets.to(dev), query_set.to(dev)
+    gathered = torch.empty((world * rows, K, d_out), dtype=torch.bfloat16, device=dev) if world > 1 else None
+
+    def step():
+        out = eng.compress(q_dev, enc, query_set=qs_dev, out_dtype=torch.bfloat16)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+            return gathered
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    assert torch.isfinite(out[:8].float()).all()
+    eng.set_profiling(True)
+    eng.reset_profile()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0 + (args.steps if world > 1 else 0)
+    prof = eng.profile()
+    eng.set_profiling(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * S / (ms_step * 1e-3)
+
+    # ---- end to end: KV tokens in pinned host memory, result back in host memory
+    e2e = None
+    if not args.no_e2e:
+        out_host = torch.empty((rows, K, d_out), dtype=torch.bfloat16, pin_memory=True)
+        eng.compress_host(q_sets, enc_host, out_host, query_set=query_set, rows_per_batch=args.e2e_rows_per_batch)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.e2e_steps):
+            eng.compress_host(q_sets, enc_host, out_host, query_set=query_set, rows_per_batch=args.e2e_rows_per_batch)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, out_host.to(dev, non_blocking=True))
+        e1.record()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms = float(te.item()) / args.e2e_steps
+        e2e = {"value": world * S / (e2e_ms * 1e-3), "unit": "video-s/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": enc_host.numel() * 2 + q_sets.numel() * 4 + query_set.numel() * 4,
+               "d2h_bytes_per_step": out_host.numel() * 2}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    f_row, f_row_kv = flops_per_row(L, d_enc, K, 0, d_out)
+    kv_ms, kv_n = prof["kv_gemm"]["ms"], prof["kv_gemm"]["launches"]
+    kv_flops_per_launch = f_row_kv * rows * args.steps / max(kv_n, 1)
+    kv_achieved = kv_flops_per_launch / (kv_ms / max(kv_n, 1) * 1e-3) / 1e12 if kv_ms > 0 else None
+    path_tflops = f_row * rows / (ms_step * 1e-3) / 1e12
+    line = {
+        "metric": "video_seconds_per_sec", "value": value, "unit": "video-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["label"], "segments_per_gpu": S, "rows_per_gpu": rows,
+                   "kv_tokens": L, "d_enc": d_enc, "d_out": d_out, "num_query": K, "num_text": 0,
+                   "parallelism": f"dp{world} (video-second ranges per GPU" + (", NCCL all-gather of compressed tokens)"
+                                                                                if world > 1 else ")"),
+                   "l2": f"inputs {enc.numel() * 2 / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
+                   "accumulate": "fp32 (TMEM), LN/softmax/residual fp32"},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "tdc_gemm_kernel (cross-attn K/V projection, all 6 layers, N=9216)", "bound": "tensor",
+                     "achieved": kv_achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": (kv_achieved / peaks["tflops_sustained"]) if kv_achieved else None, "traffic": None,
+                     "peak_source": peaks["source"] + " bf16_tflops_sustained", "launches": kv_n,
+                     "avg_launch_ms": kv_ms / max(kv_n, 1), "share_of_step": kv_ms / (ms_step * args.steps)},
+        "path": {"algorithmic_tflops": path_tflops, "frac_of_sustained_peak": path_tflops / peaks["tflops_sustained"],
+                 "gflop_per_row": f_row / 1e9,
+                 "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}},
+    }
+    if not args.no_cpu_baseline:
+        v, dt, cores = cpu_baseline(geom, sd, w, args.cpu_sample_rows, 99)
+        line["cpu_baseline"] = {"value": v, "unit": "video-s/s", "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_sample_rows} rows of the same workload in {dt:.1f} s "
+                                          f"(oracle port of the reference, fp32 torch, one batch)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -178,8 +178,7 @@ class TDCCompressor(nn.Module):
         L = Lv + La
         if La:
             enc = torch.empty((R, L, d), dtype=dtype, device=dev)
-            torch.index_select(visual_emb_frame, 0, row_idx, out=enc[:, :Lv]) if False else enc[:, :Lv].copy_(
-                visual_emb_frame.index_select(0, row_idx))
+            enc[:, :Lv].copy_(visual_emb_frame.index_select(0, row_idx))
             enc[:, Lv:].copy_(audio_tok.index_select(0, row_idx))
             static_tok = torch.cat([visual_emb_frame.index_select(0, static_idx),
                                     audio_tok.index_select(0, static_idx)], dim=1)  # [C, L, d]

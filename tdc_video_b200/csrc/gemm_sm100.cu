@@ -13,14 +13,17 @@
 //     static round-robin over output tiles, N fastest so that the concurrently
 //     running tiles share a handful of A row-panels while W stays L2-resident;
 //   * warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
-//     tcgen05.mma issuer, warps 2-5 = epilogue (one TMEM lane quadrant each);
+//     tcgen05.mma issuer, warps 2-9 = epilogue (TMEM lane quadrant x column half each);
 //   * STAGES-deep smem ring of 128B-swizzled K-major tiles (A 128x64, W BLOCK_N/CG x64)
 //     with full/empty mbarriers; tcgen05.commit releases a slot as soon as the MMAs
 //     that read it have retired;
 //   * fp32 accumulators in TMEM, double buffered (2 x BLOCK_N columns) so the
 //     epilogue of tile i overlaps the mainloop of tile i+1;
-//   * epilogue fused into the drain: +bias, exact-erf GELU, fp32 residual add,
-//     bf16 / fp32 stores straight from registers (each thread owns one output row).
+//   * epilogue fused into the drain: +bias, exact-erf GELU, bf16 / fp32 conversion; each
+//     thread owns one output row, writes 128-byte row pieces into a 128B-swizzled smem
+//     staging tile (bank-conflict free) and one lane hands the 32-row tile to the TMA
+//     store engine — fully coalesced global writes, clipped at the M/N edges by hardware,
+//     double-buffered so the next TMEM drain overlaps the store.
 #include "tdc_gemm.cuh"
 #include "tdc_ptx.cuh"
 #include "tdc_b200.h"
@@ -34,15 +37,14 @@ namespace {
 constexpr int kBlockM = 128;  // rows per CTA (UMMA M = 128 * CG)
 constexpr int kBlockK = 64;   // one 128-byte swizzle span of bf16
 constexpr int kUmmaK = 16;
-constexpr int kNumThreads = 192;
+constexpr int kNumEpilogueWarps = 8;
+constexpr int kNumThreads = 64 + 32 * kNumEpilogueWarps;
 constexpr int kAccStages = 2;
+constexpr int kStoreTileBytes = 32 * 128;  // 32 rows x 128 B, one TMA store box
+constexpr int kStoreBufs = 2;              // per epilogue warp
 
 struct EpilogueArgs {
-  void* out;
-  long long ldo;
   const float* bias;
-  const float* resid;
-  long long ldr;
   int mode;
 };
 
@@ -52,58 +54,60 @@ struct SmemLayout {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarrierOffset = STAGES * kStageBytes;
+  static constexpr int kStagingOffset = STAGES * kStageBytes;
+  static constexpr int kStagingBytes = kNumEpilogueWarps * kStoreBufs * kStoreTileBytes;
+  static constexpr int kBarrierOffset = kStagingOffset + kStagingBytes;
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem base ptr
   static constexpr int kBarrierBytes = (2 * STAGES + 2 * kAccStages) * 8 + 16;
   static constexpr int kTotalBytes = kBarrierOffset + kBarrierBytes + 1024;  // + manual 1024 B alignment slack
 };
 
+// acc (+bias) for 8 consecutive columns starting at `col` (bias may be null; columns >= n read no bias)
+__device__ __forceinline__ void load_bias8(const float* bias, int col, int n, float (&b)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] = 0.f;
+  if (bias != nullptr && col < n) {  // n % 8 == 0: a group of 8 is either fully inside or fully outside
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+  }
+}
+
+// Write one thread's 32 accumulator columns (already in registers) into its row of the
+// 128B-swizzled staging tile: 16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) * 16).
+// bf16 modes: the 32 columns are 64 B = chunks [chunk0, chunk0+4); fp32: 128 B = chunks [0, 8).
 template <int MODE>
-__device__ __forceinline__ void epilogue_store_32(const uint32_t (&v)[32], long long row, int col0, int n,
-                                                  const EpilogueArgs& e) {
+__device__ __forceinline__ void stage_32_columns(const uint32_t (&v)[32], uint8_t* tile, uint32_t lane, int chunk0,
+                                                 const float* bias, int col0, int n) {
+  uint8_t* row = tile + lane * 128;
+  const uint32_t sw = lane & 7;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const int col = col0 + g * 8;
-    if (col >= n) break;
-    float x[8];
+    float b[8], x[8];
+    load_bias8(bias, col0 + g * 8, n, b);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
-    if (e.bias != nullptr) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col + 4));
-      x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-      x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+    for (int j = 0; j < 8; ++j) {
+      x[j] = __uint_as_float(v[g * 8 + j]) + b[j];
+      if (MODE == EPI_BIAS_GELU_BF16) x[j] = gelu_erf_fast(x[j]);
     }
-    if (MODE == EPI_BIAS_GELU_BF16) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
-    }
-    if (MODE == EPI_BIAS_RESID_F32) {
-      if (e.resid != nullptr) {
-        const float4 r0 = *reinterpret_cast<const float4*>(e.resid + row * e.ldr + col);
-        const float4 r1 = *reinterpret_cast<const float4*>(e.resid + row * e.ldr + col + 4);
-        x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
-        x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
-      }
-      float* o = reinterpret_cast<float*>(e.out) + row * e.ldo + col;
-      *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
+    if (MODE == EPI_BIAS_F32) {
+      *reinterpret_cast<float4*>(row + (((2 * g) ^ sw) << 4)) = make_float4(x[0], x[1], x[2], x[3]);
+      *reinterpret_cast<float4*>(row + (((2 * g + 1) ^ sw) << 4)) = make_float4(x[4], x[5], x[6], x[7]);
     } else {
       uint4 pk;
       pk.x = pack_bf16x2(x[0], x[1]);
       pk.y = pack_bf16x2(x[2], x[3]);
       pk.z = pack_bf16x2(x[4], x[5]);
       pk.w = pack_bf16x2(x[6], x[7]);
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) + row * e.ldo + col;
-      *reinterpret_cast<uint4*>(o) = pk;
+      *reinterpret_cast<uint4*>(row + (((chunk0 + g) ^ sw) << 4)) = pk;
     }
   }
 }
 
 template <int CG, int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kNumThreads, 1)
-tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int m, int n,
-                int k, EpilogueArgs epi) {
+tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ CUtensorMap map_c, int m, int n, int k, EpilogueArgs epi) {
   using L = SmemLayout<CG, BLOCK_N, STAGES>;
   constexpr uint32_t kTmemCols = kAccStages * BLOCK_N;  // 512 (BLOCK_N=256) or 256
   constexpr uint32_t kIdesc = make_idesc_bf16_f32(kBlockM * CG, BLOCK_N);
@@ -133,6 +137,7 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -141,7 +146,7 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4 * CG);  // one elected lane per epilogue warp (of both CTAs)
+      mbar_init(&tmem_empty_bar[s], kNumEpilogueWarps * CG);  // one lane per epilogue warp (of both CTAs)
     }
     fence_mbar_init();
   }
@@ -214,29 +219,77 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else {
     // ===================== epilogue warps =====================
-    const uint32_t quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // warp -> (TMEM lane quadrant = warp % 4 [hardware rule], column half of the tile)
+    const uint32_t quad = warp & 3;
+    const uint32_t half = (warp - 2) >> 2;
+    constexpr int kHalfCols = BLOCK_N / 2;
+    uint8_t* staging = smem + L::kStagingOffset + (warp - 2) * (kStoreBufs * kStoreTileBytes);
+    const bool f32_out = (epi.mode == EPI_BIAS_F32);
+    int sbuf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (long long tile = first_tile; tile < num_tiles; tile += tile_stride) {
       const int tm = static_cast<int>(tile / num_n_tiles);
       const int tn = static_cast<int>(tile % num_n_tiles);
-      const long long row = static_cast<long long>(tm) * tile_m_rows + cta_rank * kBlockM + quad * 32 + lane;
-      const int col_base = tn * BLOCK_N;
+      const int row0 = tm * tile_m_rows + static_cast<int>(cta_rank) * kBlockM + static_cast<int>(quad) * 32;
+      const int col_base = tn * BLOCK_N + static_cast<int>(half) * kHalfCols;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after_sync();
-      const uint32_t t_addr = tmem_base + ((quad * 32u) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+      const uint32_t t_addr = tmem_base + ((quad * 32u) << 16) + static_cast<uint32_t>(acc * BLOCK_N) + half * kHalfCols;
+      const bool live = row0 < m;  // warp-uniform: this 32-row slab has at least one real row
+      if (f32_out) {
+        // 32 fp32 columns = one 128-byte staging row per store
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_addr + c * 32, v);
-        tmem_ld_wait();
-        if (row < m) {
+        for (int c = 0; c < kHalfCols / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + c * 32, v);
+          tmem_ld_wait();
           const int col0 = col_base + c * 32;
-          if (epi.mode == EPI_BIAS_BF16) epilogue_store_32<EPI_BIAS_BF16>(v, row, col0, n, epi);
-          else if (epi.mode == EPI_BIAS_GELU_BF16) epilogue_store_32<EPI_BIAS_GELU_BF16>(v, row, col0, n, epi);
-          else epilogue_store_32<EPI_BIAS_RESID_F32>(v, row, col0, n, epi);
+          if (live && col0 < n) {
+            if (lane == 0) tma_store_wait_read<kStoreBufs - 1>();  // staging[sbuf] no longer being read
+            __syncwarp();
+            uint8_t* tile_buf = staging + sbuf * kStoreTileBytes;
+            stage_32_columns<EPI_BIAS_F32>(v, tile_buf, lane, 0, epi.bias, col0, n);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_c, tile_buf, col0, row0);
+              tma_store_commit();
+            }
+            sbuf ^= 1;
+          }
+        }
+      } else {
+        // 64 bf16 columns (two TMEM loads) = one 128-byte staging row per store
+#pragma unroll 1
+        for (int c = 0; c < kHalfCols / 64; ++c) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(t_addr + c * 64, v0);
+          tmem_ld_32x32(t_addr + c * 64 + 32, v1);
+          tmem_ld_wait();
+          const int col0 = col_base + c * 64;
+          if (live && col0 < n) {
+            if (lane == 0) tma_store_wait_read<kStoreBufs - 1>();
+            __syncwarp();
+            uint8_t* tile_buf = staging + sbuf * kStoreTileBytes;
+            if (epi.mode == EPI_BIAS_GELU_BF16) {
+              stage_32_columns<EPI_BIAS_GELU_BF16>(v0, tile_buf, lane, 0, epi.bias, col0, n);
+              stage_32_columns<EPI_BIAS_GELU_BF16>(v1, tile_buf, lane, 4, epi.bias, col0 + 32, n);
+            } else {
+              stage_32_columns<EPI_BIAS_BF16>(v0, tile_buf, lane, 0, epi.bias, col0, n);
+              stage_32_columns<EPI_BIAS_BF16>(v1, tile_buf, lane, 4, epi.bias, col0 + 32, n);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_c, tile_buf, col0, row0);
+              tma_store_commit();
+            }
+            sbuf ^= 1;
+          }
         }
       }
+      // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) {
@@ -245,6 +298,7 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all<0>();  // smem must outlive the last bulk stores
   }
 
   // ===================== teardown =====================
@@ -277,16 +331,20 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] (pitch ld elements) -> tiles of box_rows x 64 with 128B swizzle.
-bool make_tensor_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+// 2-D row-major [rows, cols] (pitch ld elements, bf16 or fp32) -> boxes of box_rows x 128 bytes with
+// 128B swizzle (64 bf16 / 32 fp32 columns per box row).
+bool make_tensor_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows,
+                     bool f32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return false;
+  const int esz = f32 ? 4 : 2;
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * esz};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  const CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                        const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -304,9 +362,10 @@ int num_sms() {
 template <int CG, int BLOCK_N, int STAGES>
 int launch_variant(const GemmProblem& p, cudaStream_t stream, const char** err) {
   using L = SmemLayout<CG, BLOCK_N, STAGES>;
-  CUtensorMap map_a, map_w;
+  CUtensorMap map_a, map_w, map_c;
   if (!make_tensor_map(&map_a, p.a, p.m, p.k, p.lda, kBlockM) ||
-      !make_tensor_map(&map_w, p.w, p.n, p.k, p.ldw, L::kBRows)) {
+      !make_tensor_map(&map_w, p.w, p.n, p.k, p.ldw, L::kBRows) ||
+      !make_tensor_map(&map_c, p.out, p.m, p.n, p.ldo, 32, p.mode == EPI_BIAS_F32)) {
     if (err) *err = "cuTensorMapEncodeTiled failed (pointer/pitch alignment?)";
     return TDC_ECUDA;
   }
@@ -323,7 +382,7 @@ int launch_variant(const GemmProblem& p, cudaStream_t stream, const char** err) 
                           ((p.n + BLOCK_N - 1) / BLOCK_N);
   long long clusters = num_sms() / CG;
   if (tiles < clusters) clusters = tiles;
-  EpilogueArgs e{p.out, p.ldo, p.bias, p.resid, p.ldr, p.mode};
+  EpilogueArgs e{p.bias, p.mode};
 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(clusters * CG));
@@ -337,7 +396,7 @@ int launch_variant(const GemmProblem& p, cudaStream_t stream, const char** err) 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t rc = cudaLaunchKernelEx(&cfg, kernel, map_a, map_w, p.m, p.n, p.k, e);
+  const cudaError_t rc = cudaLaunchKernelEx(&cfg, kernel, map_a, map_w, map_c, p.m, p.n, p.k, e);
   if (rc != cudaSuccess) {
     if (err) *err = cudaGetErrorString(rc);
     return TDC_ECUDA;
@@ -358,21 +417,21 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, const char** err) {
     if (err) *err = "gemm: K, N and pitches must be multiples of 8 elements and pointers 16-byte aligned";
     return TDC_EINVAL;
   }
-  if (p.mode != EPI_BIAS_RESID_F32 && (p.ldo % 8) != 0) {
+  if (p.mode != EPI_BIAS_F32 && (p.ldo % 8) != 0) {
     if (err) *err = "gemm: bf16 output pitch must be a multiple of 8 elements";
     return TDC_EINVAL;
   }
-  if (p.mode < 0 || p.mode > EPI_BIAS_RESID_F32) {
+  if (p.mode < 0 || p.mode > EPI_BIAS_F32) {
     if (err) *err = "gemm: unknown epilogue mode";
     return TDC_EINVAL;
   }
   int cg = p.cta_group == 0 ? 1 : p.cta_group;
   if (p.n <= 128) {
     // narrow outputs (small test geometries): single-CTA 128x128 tiles
-    return launch_variant<1, 128, 6>(p, stream, err);
+    return launch_variant<1, 128, 4>(p, stream, err);
   }
-  if (cg == 2) return launch_variant<2, 256, 6>(p, stream, err);
-  return launch_variant<1, 256, 4>(p, stream, err);
+  if (cg == 2) return launch_variant<2, 256, 5>(p, stream, err);
+  return launch_variant<1, 256, 3>(p, stream, err);
 }
 
 }  // namespace tdc

@@ -92,9 +92,10 @@ __device__ __forceinline__ void ln_finish(float4 (&x)[kMaxVec], int nv, int lane
 }
 
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long ldx,
+                                                        const float* resid, long long ldr,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
-                                                        float* __restrict__ y_f32, __nv_bfloat16* __restrict__ y_bf16,
+                                                        float* y_f32, __nv_bfloat16* __restrict__ y_bf16,
                                                         long long ldy, long long rows, int width) {
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -105,6 +106,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 #pragma unroll
   for (int j = 0; j < kMaxVec; ++j)
     if (j < nv && lane + 32 * j < width / 4) v[j] = xr[lane + 32 * j];
+  if (resid != nullptr) {  // post-LN residual: LN(dense(x) + input), Qformer.py:285-289 / 371-375
+    const float4* rr = reinterpret_cast<const float4*>(resid + row * ldr);
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j)
+      if (j < nv && lane + 32 * j < width / 4) {
+        const float4 r = rr[lane + 32 * j];
+        v[j].x += r.x; v[j].y += r.y; v[j].z += r.z; v[j].w += r.w;
+      }
+  }
   ln_finish(v, nv, lane, width, gamma, beta, eps, y_f32 ? y_f32 + row * ldy : nullptr,
             y_bf16 ? y_bf16 + row * ldy : nullptr);
 }
@@ -232,16 +242,16 @@ int check_launch(const char** err) {
 
 }  // namespace
 
-int layernorm_launch(const float* x, long long ldx, const float* gamma, const float* beta, float eps, float* y_f32,
-                     __nv_bfloat16* y_bf16, long long ldy, long long rows, int width, cudaStream_t stream,
-                     const char** err) {
+int layernorm_launch(const float* x, long long ldx, const float* resid, long long ldr, const float* gamma,
+                     const float* beta, float eps, float* y_f32, __nv_bfloat16* y_bf16, long long ldy, long long rows,
+                     int width, cudaStream_t stream, const char** err) {
   if (rows <= 0) return TDC_OK;
-  if (width % 4 != 0 || width > kMaxVec * 128 || ldx % 4 != 0 || ldy % 4 != 0) {
+  if (width % 4 != 0 || width > kMaxVec * 128 || ldx % 4 != 0 || ldy % 4 != 0 || ldr % 4 != 0) {
     if (err) *err = "layernorm: width must be a multiple of 4 and <= 1024";
     return TDC_EINVAL;
   }
-  layernorm_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(x, ldx, gamma, beta, eps, y_f32, y_bf16,
-                                                                              ldy, rows, width);
+  layernorm_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(x, ldx, resid, ldr, gamma, beta, eps,
+                                                                              y_f32, y_bf16, ldy, rows, width);
   return check_launch(err);
 }
 

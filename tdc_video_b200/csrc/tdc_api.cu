@@ -298,11 +298,10 @@ struct ForwardCall {
   } while (0)
 
 int gemm(tdc_handle* h, int cls, cudaStream_t s, const void* a, long long lda, const void* w, long long ldw,
-         const float* bias, void* out, long long ldo, long long m, int n, int k, int mode, const float* resid,
-         long long ldr, const char** err) {
+         const float* bias, void* out, long long ldo, long long m, int n, int k, int mode, const char** err) {
   GemmProblem p;
   p.a = a; p.lda = lda; p.w = w; p.ldw = ldw; p.bias = bias; p.out = out; p.ldo = ldo;
-  p.m = static_cast<int>(m); p.n = n; p.k = k; p.mode = mode; p.resid = resid; p.ldr = ldr;
+  p.m = static_cast<int>(m); p.n = n; p.k = k; p.mode = mode;
   p.cta_group = h->cfg.gemm_cta_group == 0 ? 2 : h->cfg.gemm_cta_group;
   KernelScope ks(h, cls, s);
   return gemm_launch(p, s, err);
@@ -331,7 +330,7 @@ int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long
   // 1. every cross layer's K and V for every KV token of every row: the dominant GEMM
   if (h->n_cross > 0)
     TDC_TRY(gemm(h, TDC_K_KV_GEMM, s, enc, c.d_enc, h->w_ckv, c.d_enc, h->b_ckv, w.kv, kvw, rows * L, kvw, c.d_enc,
-                 EPI_BIAS_BF16, nullptr, 0, &err));
+                 EPI_BIAS_BF16, &err));
 
   // 2. embeddings + LayerNorm into the [query slab | text slab] layout
   {
@@ -354,15 +353,16 @@ int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long
   const long long MQ = rows * K, MT = rows * T, MA = rows * n;
   auto ln = [&](const float* g, const float* b, long long first, long long count) -> int {
     KernelScope ks(h, TDC_K_ROWOPS, s);
-    return layernorm_launch(w.pre + first * H, H, g, b, c.ln_eps, w.h_f32 + first * H, w.h_bf16 + first * H, H, count,
-                            H, s, &err);
+    // h = LN(pre + h): the residual add of the post-LN block lives here, not in the GEMM epilogue
+    return layernorm_launch(w.pre + first * H, H, w.h_f32 + first * H, H, g, b, c.ln_eps, w.h_f32 + first * H,
+                            w.h_bf16 + first * H, H, count, H, s, &err);
   };
 
   for (int l = 0; l < c.layers; ++l) {
     const LayerW& lw = h->layers[l];
     // ---- self-attention over all K+T tokens of the row
     TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16, H, lw.w_qkv, H, lw.b_qkv, w.qkv, 3 * H, MA, 3 * H, H,
-                 EPI_BIAS_BF16, nullptr, 0, &err));
+                 EPI_BIAS_BF16, &err));
     {
       AttentionArgs a;
       a.q = w.qkv; a.k = w.qkv + H; a.v = w.qkv + 2 * H; a.out = w.ctx;
@@ -374,14 +374,12 @@ int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long
       KernelScope ks(h, TDC_K_ATTENTION, s);
       TDC_TRY(attention_launch(a, s, &err));
     }
-    TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.ctx, H, lw.w_ao, H, lw.b_ao, w.pre, H, MA, H, H, EPI_BIAS_RESID_F32,
-                 w.h_f32, H, &err));
+    TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.ctx, H, lw.w_ao, H, lw.b_ao, w.pre, H, MA, H, H, EPI_BIAS_F32, &err));
     TDC_TRY(ln(lw.ln_a_g, lw.ln_a_b, 0, MA));
 
     // ---- cross-attention: query tokens only
     if (lw.cross_index >= 0) {
-      TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16, H, lw.w_cq, H, lw.b_cq, w.qc, H, MQ, H, H, EPI_BIAS_BF16,
-                   nullptr, 0, &err));
+      TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16, H, lw.w_cq, H, lw.b_cq, w.qc, H, MQ, H, H, EPI_BIAS_BF16, &err));
       AttentionArgs a;
       a.q = w.qc; a.out = w.ctx; a.ldq = H; a.ldo = H;
       a.k = w.kv + static_cast<size_t>(lw.cross_index) * 2 * H;
@@ -396,22 +394,20 @@ int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long
         KernelScope ks(h, TDC_K_ATTENTION, s);
         TDC_TRY(attention_launch(a, s, &err));
       }
-      TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.ctx, H, lw.w_co, H, lw.b_co, w.pre, H, MQ, H, H, EPI_BIAS_RESID_F32,
-                   w.h_f32, H, &err));
+      TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.ctx, H, lw.w_co, H, lw.b_co, w.pre, H, MQ, H, H, EPI_BIAS_F32, &err));
       TDC_TRY(ln(lw.ln_c_g, lw.ln_c_b, 0, MQ));
     }
 
     // ---- feed-forward: query tokens and text tokens use different weights
     TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16, H, lw.w_fq1, H, lw.b_fq1, w.mid, I, MQ, I, H, EPI_BIAS_GELU_BF16,
-                 nullptr, 0, &err));
-    TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.mid, I, lw.w_fq2, I, lw.b_fq2, w.pre, H, MQ, H, I, EPI_BIAS_RESID_F32,
-                 w.h_f32, H, &err));
+                 &err));
+    TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.mid, I, lw.w_fq2, I, lw.b_fq2, w.pre, H, MQ, H, I, EPI_BIAS_F32, &err));
     TDC_TRY(ln(lw.ln_fq_g, lw.ln_fq_b, 0, MQ));
     if (T > 0) {
       TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16 + MQ * H, H, lw.w_ft1, H, lw.b_ft1, w.mid, I, MT, I, H,
-                   EPI_BIAS_GELU_BF16, nullptr, 0, &err));
+                   EPI_BIAS_GELU_BF16, &err));
       TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.mid, I, lw.w_ft2, I, lw.b_ft2, w.pre + MQ * H, H, MT, H, I,
-                   EPI_BIAS_RESID_F32, w.h_f32 + MQ * H, H, &err));
+                   EPI_BIAS_F32, &err));
       TDC_TRY(ln(lw.ln_ft_g, lw.ln_ft_b, MQ, MT));
     }
   }
@@ -424,7 +420,7 @@ int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long
   } else {
     // vision_proj on the (contiguous) query slab, then unit-normalise every token
     TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16, H, h->w_vp, H, h->b_vp, w.proj, c.d_out, MQ, c.d_out, H,
-                 EPI_BIAS_RESID_F32, nullptr, 0, &err));
+                 EPI_BIAS_F32, &err));
     const size_t osz = f.out_dtype == TDC_F32 ? 4 : 2;
     void* out = static_cast<uint8_t*>(f.out) + static_cast<size_t>(row0) * K * c.d_out * osz;
     KernelScope ks(h, TDC_K_ROWOPS, s);
@@ -612,7 +608,7 @@ int tdc_proj_norm(tdc_handle* h, const void* hidden, int32_t hidden_dtype, int32
     TDC_TRY(take_query_tokens_launch(hidden, hidden_dtype, rows, tokens_per_row, num_query, c.hidden, x, s, &err));
   }
   TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, x, c.hidden, h->w_vp, c.hidden, h->b_vp, y, c.d_out, M, c.d_out, c.hidden,
-               EPI_BIAS_RESID_F32, nullptr, 0, &err));
+               EPI_BIAS_F32, &err));
   KernelScope ks(h, TDC_K_ROWOPS, s);
   TDC_TRY(l2_normalize_launch(y, c.d_out, out, out_dtype, M, c.d_out, s, &err));
   return TDC_OK;
@@ -626,7 +622,7 @@ int tdc_linear(const void* x, const void* w, const float* bias, void* y, int32_t
   p.a = x; p.lda = k; p.w = w; p.ldw = k; p.bias = bias; p.out = y; p.ldo = n; p.m = m; p.n = n; p.k = k;
   if (out_dtype == TDC_F32) {
     if (gelu) { g_create_error = "tdc_linear: gelu needs bf16 output"; return TDC_EINVAL; }
-    p.mode = EPI_BIAS_RESID_F32;
+    p.mode = EPI_BIAS_F32;
   } else if (out_dtype == TDC_BF16) {
     p.mode = gelu ? EPI_BIAS_GELU_BF16 : EPI_BIAS_BF16;
   } else { g_create_error = "tdc_linear: out_dtype must be bf16 or fp32"; return TDC_EINVAL; }

@@ -13,7 +13,7 @@ namespace tdc {
 enum GemmEpilogueMode : int {
   EPI_BIAS_BF16 = 0,       // out bf16  = acc + bias
   EPI_BIAS_GELU_BF16 = 1,  // out bf16  = gelu_erf(acc + bias)
-  EPI_BIAS_RESID_F32 = 2,  // out fp32  = acc + bias (+ resid fp32 if non-null)
+  EPI_BIAS_F32 = 2,        // out fp32  = acc + bias (the residual add lives in the LayerNorm kernel)
 };
 
 struct GemmProblem {
@@ -23,9 +23,7 @@ struct GemmProblem {
   int m = 0, n = 0, k = 0;
   void* out = nullptr;  // bf16 or fp32 [M, N], row pitch ldo elements
   long long ldo = 0;
-  const float* bias = nullptr;   // [N] or null
-  const float* resid = nullptr;  // fp32 [M, N] pitch ldr, or null (mode 2 only)
-  long long ldr = 0;
+  const float* bias = nullptr;  // [N] or null
   int mode = EPI_BIAS_BF16;
   int cta_group = 0;  // 0 = library default, 1 = single-CTA tiles, 2 = CTA-pair (cta_group::2) tiles
 };

@@ -31,11 +31,12 @@ struct AttentionArgs {
 };
 int attention_launch(const AttentionArgs& a, cudaStream_t stream, const char** err);
 
-// y = LayerNorm(x) * gamma + beta, fp32 statistics (tdc/Qformer.py:285-289, 371-375).
-// x fp32 [rows, width]; writes y as fp32 (nullable) and bf16 (nullable).
-int layernorm_launch(const float* x, long long ldx, const float* gamma, const float* beta, float eps, float* y_f32,
-                     __nv_bfloat16* y_bf16, long long ldy, long long rows, int width, cudaStream_t stream,
-                     const char** err);
+// y = LayerNorm(x + resid) * gamma + beta, fp32 statistics (tdc/Qformer.py:285-289, 371-375).
+// x, resid (nullable) fp32 [rows, width]; writes y as fp32 (nullable) and bf16 (nullable).
+// y_f32 may alias resid (each warp reads its whole row before writing it).
+int layernorm_launch(const float* x, long long ldx, const float* resid, long long ldr, const float* gamma,
+                     const float* beta, float eps, float* y_f32, __nv_bfloat16* y_bf16, long long ldy, long long rows,
+                     int width, cudaStream_t stream, const char** err);
 
 // BertEmbeddings.forward (tdc/Qformer.py:78-108): query tokens = query_embeds (no position
 // embedding), text tokens = word_emb[id] + pos_emb[t]; LayerNorm over everything.

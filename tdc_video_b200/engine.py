@@ -145,6 +145,54 @@ class QFormerEngine:
         return self._run(self.lib.tdc_compress, "tdc_compress", query_embeds, enc, input_ids, query_set, text_set,
                          kv_len, self.cfg.d_out, lambda K, T: K, out_dtype)
 
+    def compress_host(self, query_embeds: torch.Tensor, enc_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
+                      *, query_set: Optional[torch.Tensor] = None, input_ids: Optional[torch.Tensor] = None,
+                      text_set: Optional[torch.Tensor] = None, rows_per_batch: int = 1024) -> torch.Tensor:
+        """`compress` for inputs that live in (pinned) HOST memory: enc_host [rows, L, d_enc] is streamed
+        to the GPU in row batches on a copy stream while the previous batch computes, and each batch's
+        [n, K, d_out] result is copied back to `out_host` on a third stream.  Stream-ordered: the
+        result is complete once the current stream is synchronised."""
+        rows, L, _ = enc_host.shape
+        K = query_embeds.shape[1]
+        dev = self.device
+        if out_host is None:
+            out_host = torch.empty((rows, K, self.cfg.d_out), dtype=enc_host.dtype, pin_memory=True)
+        if rows == 0:
+            return out_host
+        rb = max(1, min(rows_per_batch, rows))
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_h2d_stream"):
+            self._h2d_stream, self._d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        stage = [torch.empty((rb, L, self.cfg.d_enc), dtype=enc_host.dtype, device=dev) for _ in range(2)]
+        h2d_done = [torch.cuda.Event() for _ in range(2)]
+        compute_done = [torch.cuda.Event() for _ in range(2)]
+        q_dev = query_embeds.to(dev, non_blocking=True)
+        qs_dev = None if query_set is None else query_set.to(dev, torch.int32)
+        ts_dev = None if text_set is None else text_set.to(dev, torch.int32)
+        ids_dev = None if input_ids is None else input_ids.to(dev)
+        self._h2d_stream.wait_stream(cur)
+        for i, r0 in enumerate(range(0, rows, rb)):
+            r1, b = min(r0 + rb, rows), i % 2
+            with torch.cuda.stream(self._h2d_stream):
+                if i >= 2:
+                    self._h2d_stream.wait_event(compute_done[b])   # staging buffer free again
+                stage[b][: r1 - r0].copy_(enc_host[r0:r1], non_blocking=True)
+                h2d_done[b].record(self._h2d_stream)
+            cur.wait_event(h2d_done[b])
+            out_dev = self.compress(q_dev if qs_dev is not None else q_dev[r0:r1], stage[b][: r1 - r0],
+                                    ids_dev if (ids_dev is None or ts_dev is not None) else ids_dev[r0:r1],
+                                    query_set=None if qs_dev is None else qs_dev[r0:r1],
+                                    text_set=None if ts_dev is None else ts_dev[r0:r1], out_dtype=out_host.dtype)
+            compute_done[b].record(cur)
+            with torch.cuda.stream(self._d2h_stream):
+                self._d2h_stream.wait_event(compute_done[b])
+                out_host[r0:r1].copy_(out_dev, non_blocking=True)
+                out_dev.record_stream(self._d2h_stream)
+        cur.wait_stream(self._d2h_stream)
+        for t in stage:
+            t.record_stream(self._h2d_stream)
+        return out_host
+
     def proj_norm(self, hidden: torch.Tensor, num_query: int, out_dtype=None) -> torch.Tensor:
         rows, tokens, H = hidden.shape
         hidden = hidden.to(self.device).contiguous()

@@ -135,10 +135,11 @@ class TDCBertModel(nn.Module):
         self._engine_key = None
         return out
 
-    def engine(self, d_out: int = 0, extra_state=None) -> QFormerEngine:
-        """The libtdc handle holding this module's weights (rebuilt when they move/change)."""
+    def engine(self, d_out: int = 0, extra_state=None, extra_key=None) -> QFormerEngine:
+        """The libtdc handle holding this module's weights (rebuilt when they move/change).
+        `extra_state` adds sibling tensors (vision_proj.*); `extra_key` identifies their version."""
         p = self.embeddings.LayerNorm.weight
-        key = (p.device, d_out, None if extra_state is None else id(extra_state))
+        key = (p.device, d_out, extra_key)
         if self._engine is None or self._engine_key != key:
             if p.device.type != "cuda":
                 raise RuntimeError("TDCBertModel runs on a CUDA (sm_100a) device only: move the module to the GPU; "

@@ -1,0 +1,146 @@
+"""The reference-shaped modules (TDCBertModel / TDCQFormer / TDCCompressor) on the GPU against the
+oracle: same state_dict names, same forward keywords, same token sequence."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import driver_oracle
+from oracle import qformer_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _metrics_ok(test, ref, what):
+    m = oracle.parity_metrics(test.float().cpu(), ref)
+    print(what, m)
+    assert m["min_cos"] >= 0.999 and m["max_abs_over_max_ref"] <= 2e-2, (what, m)
+
+
+def _small_cfg(**kw):
+    from tdc_video_b200.qformer import QFormerConfig
+    base = dict(vocab_size=40, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                max_position_embeddings=16, encoder_width=64, query_length=16)
+    base.update(kw)
+    return QFormerConfig(**base)
+
+
+def _geom_of(cfg, d_out):
+    from oracle.synth import QFormerGeometry
+    return QFormerGeometry(hidden=cfg.hidden_size, heads=cfg.num_attention_heads, intermediate=cfg.intermediate_size,
+                           layers=cfg.num_hidden_layers, cross_freq=cfg.cross_attention_freq, d_enc=cfg.encoder_width,
+                           d_out=d_out, vocab=cfg.vocab_size, max_pos=cfg.max_position_embeddings,
+                           ln_eps=cfg.layer_norm_eps)
+
+
+def _randomize(module, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if name.endswith("LayerNorm.weight"):
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g))
+            elif p.dim() == 1:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * (0.5 / p.shape[-1] ** 0.5))
+
+
+def test_bert_mirror_forward_signature_and_parity():
+    from tdc_video_b200.qformer import TDCQFormer
+    cfg = _small_cfg()
+    model = TDCQFormer(cfg)
+    _randomize(model, 1)
+    model = model.cuda().eval()
+    sd = {k[len("bert."):]: v.detach().cpu() for k, v in model.state_dict().items() if k.startswith("bert.")}
+    B, K, T, L = 5, 16, 4, 21
+    q = torch.randn(B, K, 128, device="cuda")
+    enc = torch.randn(B, L, 64, device="cuda")
+    ids = torch.randint(0, 40, (B, T), device="cuda")
+    atts = torch.ones(B, L, dtype=torch.long, device="cuda")
+    out = model.bert(input_ids=ids, query_embeds=q, encoder_hidden_states=enc, encoder_attention_mask=atts,
+                     use_cache=False, return_dict=True)          # the call of cambrian_arch.py:1653-1662
+    assert out.last_hidden_state.shape == (B, K + T, 128) and out.last_hidden_state.dtype == q.dtype
+    ref = oracle.qformer_forward(sd, _geom_of(cfg, 0), q.cpu(), enc.cpu(), ids.cpu())
+    _metrics_ok(out.last_hidden_state, ref, "bert mirror")
+    # weights changed in place + invalidate -> new result
+    with torch.no_grad():
+        model.bert.encoder.layer[0].output_query.dense.bias.add_(1.0)
+    model.bert.invalidate_engine()
+    out2 = model.bert(query_embeds=q, encoder_hidden_states=enc, input_ids=ids).last_hidden_state
+    assert not torch.allclose(out2, out.last_hidden_state)
+    with pytest.raises(NotImplementedError):
+        model.bert(query_embeds=q, encoder_hidden_states=enc, attention_mask=torch.ones(B, K, device="cuda"))
+    with pytest.raises(RuntimeError, match="inference-only"):
+        model.train().bert(query_embeds=q, encoder_hidden_states=enc)
+
+
+def test_state_dict_names_match_reference_layout():
+    """Key names/shapes of SURVEY.md appendix A, incl. the unused LM head, so reference checkpoints load strictly."""
+    from tdc_video_b200.qformer import TDCQFormer
+    cfg = _small_cfg()
+    keys = dict(TDCQFormer(cfg).state_dict())
+    for k in ["bert.embeddings.word_embeddings.weight", "bert.embeddings.position_embeddings.weight",
+              "bert.embeddings.LayerNorm.weight", "bert.embeddings.position_ids",
+              "bert.encoder.layer.0.attention.self.query.weight", "bert.encoder.layer.0.attention.output.LayerNorm.bias",
+              "bert.encoder.layer.0.crossattention.self.key.weight", "bert.encoder.layer.0.crossattention.output.dense.bias",
+              "bert.encoder.layer.1.intermediate.dense.weight", "bert.encoder.layer.1.output.LayerNorm.weight",
+              "bert.encoder.layer.1.intermediate_query.dense.bias", "bert.encoder.layer.1.output_query.dense.weight",
+              "cls.predictions.bias", "cls.predictions.transform.dense.weight", "cls.predictions.decoder.weight"]:
+        assert k in keys, k
+    assert "bert.encoder.layer.1.crossattention.self.key.weight" not in keys     # cross_attention_freq = 2
+    assert keys["bert.encoder.layer.0.crossattention.self.key.weight"].shape == (128, 64)
+
+
+@pytest.mark.parametrize("query_type,text,audio,keep_static", [("Avg_pool", True, True, True),
+                                                                 ("Avg_pool", False, False, True),
+                                                                 ("learned", True, False, False)])
+def test_compressor_matches_reference_loop(query_type, text, audio, keep_static):
+    from tdc_video_b200.compressor import TDCCompressor
+    cfg = _small_cfg()
+    d = 64
+    comp = TDCCompressor(d, context_token_num=16, query_type=query_type, text_input=text, add_static=keep_static,
+                         audio_input=audio, qformer_config=cfg)
+    _randomize(comp, 2)
+    comp = comp.cuda().eval()
+    sizes = [3, 1, 12, 8, 2]
+    n, Lv, La = sum(sizes), 20, 6
+    frames = torch.randn(n, Lv, d, device="cuda")
+    audio_frames = torch.randn(n, La, 768, device="cuda") if audio else None
+    ids = torch.randint(0, 40, (1, 5), device="cuda") if text else None
+    weights = {k[len("Qformer.bert."):]: v.detach().cpu() for k, v in comp.state_dict().items()
+               if k.startswith("Qformer.bert.")}
+    for k, v in comp.state_dict().items():
+        if not k.startswith("Qformer."):
+            weights[k] = v.detach().cpu()
+    for budget in (None, 150):
+        seq = comp.compress_video(frames, sizes, input_ids=ids, audio_frames=audio_frames, max_visual_len=budget)
+        ref = driver_oracle.compress_video(weights, _geom_of(cfg, d), frames.cpu(), sizes, context_token_num=16,
+                                           query_type=query_type, add_text=text, keep_static=keep_static,
+                                           input_ids=None if ids is None else ids.cpu(),
+                                           audio_frames=None if audio_frames is None else audio_frames.cpu(),
+                                           max_visual_len=budget)
+        assert seq.shape == ref.shape
+        _metrics_ok(seq, ref, f"compressor {query_type} text={text} audio={audio} budget={budget}")
+
+
+def test_gelu_mlp_projector_and_linear():
+    """mm_projector Linear-GELU(erf)-Linear (cambrian_arch.py:65-69) on the tcgen05 GEMM."""
+    from tdc_video_b200 import linear
+    torch.manual_seed(0)
+    x = torch.randn(1000, 1024, device="cuda")
+    w0, b0 = torch.randn(3584, 1024, device="cuda") * 0.03, torch.randn(3584, device="cuda") * 0.1
+    w1, b1 = torch.randn(3584, 3584, device="cuda") * 0.02, torch.randn(3584, device="cuda") * 0.1
+    mid = linear(x, w0, b0, gelu=True)
+    y = linear(mid, w1, b1, out_dtype=torch.float32)
+    ref = oracle.gelu_mlp(w0.cpu(), b0.cpu(), w1.cpu(), b1.cpu(), x.cpu())
+    _metrics_ok(y, ref, "gelu mlp")
+    for cg in (1, 2):
+        y1 = linear(x, w0, b0, out_dtype=torch.float32, cta_group=cg)
+        _metrics_ok(y1, torch.nn.functional.linear(x.cpu(), w0.cpu(), b0.cpu()), f"linear cg{cg}")
+
+
+def test_avg_pool_tokens_matches_adaptive_avg_pool1d():
+    from tdc_video_b200 import avg_pool_tokens
+    x = torch.randn(7, 156, 64, device="cuda")
+    got = avg_pool_tokens(x, 16).float().cpu()
+    ref = oracle.avg_pool_queries(x.cpu(), 16)
+    assert torch.allclose(got, ref, atol=1e-2, rtol=1e-2)
