@@ -30,6 +30,14 @@ import torch.nn.functional as F
 from . import qformer_oracle as qo
 
 
+def segment_sizes_from_boundaries(segment_frame_indices, n_frames: int):
+    """cambrian_arch.py:1541-1544: boundaries after frames `segment_frame_indices` ->
+    frames per segment (empty segments are possible and skipped by the loop, :1604-1605)."""
+    seg = (torch.as_tensor(segment_frame_indices).long() + 1).tolist()
+    points = [0] + seg + [int(n_frames)]
+    return [points[i + 1] - points[i] for i in range(len(points) - 1)]
+
+
 def compress_video(weights: Dict[str, object], geom, visual_emb_frame, segment_sizes: Sequence[int], *,
                    context_token_num: int = 16, query_type: str = "Avg_pool", add_text: bool = True,
                    keep_static: bool = True, add_sep: bool = True, input_ids=None, audio_frames=None,

@@ -70,6 +70,70 @@ def run_reference(geom, sd_np, inputs, num_query, kv_len=None):
     return hidden.numpy(), comp.numpy()
 
 
+# ---- driver goldens: the REAL prepare_inputs_labels_for_multimodal through oracle/harness.py ------------
+DRIVER_D = 48
+DRIVER_GEOM = QFormerGeometry(hidden=64, heads=1, intermediate=96, layers=2, cross_freq=2, d_enc=DRIVER_D,
+                              d_out=DRIVER_D, vocab=40, max_pos=16)
+# name -> (n_frames, K, query_type, text, add_static, tokenizer_model_max_length)
+DRIVER_CASES = {
+    "avgpool_text_33f": (33, 8, "Avg_pool", True, True, 100000),
+    "learned_notext_budget_30f": (30, 8, "learned", False, True, 2600),
+}
+
+
+def driver_weights(seed, K):
+    """Q-Former + the sibling tensors the driver touches, all from one numpy RandomState."""
+    rs = np.random.RandomState(seed)
+    w = make_state_dict(DRIVER_GEOM, seed, stress=4.0)
+    f = lambda *s: (rs.standard_normal(s) * 0.3).astype(np.float32)
+    w.update({"query_proj.weight": f(64, DRIVER_D), "query_proj.bias": f(64), "frame_seg": f(DRIVER_D),
+              "image_newline": f(DRIVER_D), "query_tokens": f(1, K, 64), "mm_projector.weight": f(DRIVER_D, 24),
+              "mm_projector.bias": f(DRIVER_D), "embed_tokens": f(10, DRIVER_D)})
+    return w
+
+
+def driver_tables(seed, n):
+    """Stub tower outputs: SigLIP-like [n,144,8] noise, DINO-like [n,144,16] slow drift with jumps."""
+    rs = np.random.RandomState(seed)
+    base = rs.standard_normal((n, 144, 8)).astype(np.float32)
+    dino = np.cumsum(rs.standard_normal((n, 1, 16)) * 0.2, axis=0) + rs.standard_normal((1, 144, 16))
+    jumps = rs.choice(n, size=max(1, n // 9), replace=False)
+    dino[jumps] += rs.standard_normal((len(jumps), 1, 16)) * 3
+    return base, dino.astype(np.float32)
+
+
+def driver_frames(w, sig, dino):
+    """What cambrian_arch.py:1146-1299 turns the tower features into for square frames:
+    mm_projector(cat(siglip, dino)) on the 12x12 grid + one image_newline per grid row -> [n,156,d]."""
+    feats = torch.from_numpy(np.concatenate([sig, dino], -1))
+    proj = F.linear(feats, torch.from_numpy(w["mm_projector.weight"]), torch.from_numpy(w["mm_projector.bias"]))
+    n = proj.shape[0]
+    proj = proj.view(n, 12, 12, -1)
+    nl = torch.from_numpy(w["image_newline"]).view(1, 1, 1, -1).expand(n, 12, 1, -1)
+    return torch.cat([proj, nl], dim=2).flatten(1, 2)
+
+
+def make_driver_goldens(only=None):
+    from oracle import harness
+    for name, (n, K, qt, text, static, max_len) in DRIVER_CASES.items():
+        if only and name not in only:
+            continue
+        w = driver_weights(40 + n, K)
+        sig, dino = driver_tables(50 + n, n)
+        ref = harness.run_reference_driver(w, DRIVER_GEOM, n, d_llm=DRIVER_D, context_token_num=K, query_type=qt,
+                                           text_input=text, add_static=static, tokenizer_model_max_length=max_len,
+                                           prompt_ids=[[3, 9, 4, 1]], siglip_table=sig, dino_table=dino)
+        assert torch.allclose(ref["frames"], driver_frames(w, sig, dino), atol=1e-6)
+        meta = dict(n_frames=n, num_query=K, query_type=qt, text=text, add_static=static,
+                    tokenizer_model_max_length=max_len, max_visual_len=max_len - 16 - 3, prompt_ids=[3, 9, 4, 1],
+                    weight_seed=40 + n, table_seed=50 + n,
+                    generator="oracle/make_golden.py: reference prepare_inputs_labels_for_multimodal via oracle/harness.py")
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"driver_{name}.npz"), meta=json.dumps(meta),
+                            segment_frame_indices=ref["segment_frame_indices"].numpy().astype(np.int64),
+                            visual_tokens=ref["visual_tokens"].numpy().astype(np.float32))
+        print(f"driver {name}: tokens {tuple(ref['visual_tokens'].shape)}")
+
+
 def main(only=None):
     assert ref_shim.reference_available(), "needs /root/reference"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -87,6 +151,7 @@ def main(only=None):
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"qformer_{name}.npz"), meta=json.dumps(meta),
                             hidden=hidden.astype(np.float32), compressed=comp.astype(np.float32))
         print(f"{name}: hidden {hidden.shape} compressed {comp.shape}")
+    make_driver_goldens(only)
 
 
 if __name__ == "__main__":

@@ -25,6 +25,7 @@ import numpy as np
 import torch
 from torch import nn
 
+from . import dist as tdist
 from .engine import avg_pool_tokens, linear
 from .qformer import QFormerConfig, TDCQFormer
 
@@ -147,11 +148,15 @@ class TDCCompressor(nn.Module):
     @torch.no_grad()
     def compress_video(self, visual_emb_frame: torch.Tensor, segment_sizes: Sequence[int],
                        input_ids: Optional[torch.Tensor] = None, audio_frames: Optional[torch.Tensor] = None,
-                       max_visual_len: Optional[int] = None, return_parts: bool = False):
+                       max_visual_len: Optional[int] = None, return_parts: bool = False, group=None,
+                       shard: bool = False):
         """visual_emb_frame [n_frames, Lv, d] (one video), segment_sizes (frames per DINO segment),
         input_ids [1, T] BERT ids of the prompt (used iff text_input), audio_frames [n_frames, La, 768]
         per-frame BEATs tokens (iff the video has audio).  Returns the token sequence
-        `new_visual_emb_frames[:max_visual_len]` of cambrian_arch.py:1694-1709."""
+        `new_visual_emb_frames[:max_visual_len]` of cambrian_arch.py:1694-1709.
+
+        shard=True (inside an initialised torch.distributed job): every rank holds the same inputs,
+        compresses a contiguous range of chunks and one all-gather assembles all rows on every rank."""
         if self.training:
             raise RuntimeError("TDCCompressor is inference-only (eval mode)")
         if not visual_emb_frame.is_cuda:
@@ -196,7 +201,20 @@ class TDCCompressor(nn.Module):
             if self.text_input and input_ids is not None and input_ids.numel() > 0:
                 ids = input_ids.reshape(1, -1)
                 text_set = torch.zeros(R, dtype=torch.int32)
-            comp = self._engine().compress(q_sets, enc, ids, query_set=query_set, text_set=text_set, out_dtype=dtype)
+            sharded = shard and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size(group) > 1
+            if not sharded:
+                comp = self._engine().compress(q_sets, enc, ids, query_set=query_set, text_set=text_set,
+                                               out_dtype=dtype)
+            else:
+                world, rank = torch.distributed.get_world_size(group), torch.distributed.get_rank(group)
+                ranges = tdist.shard_chunk_ranges(plan.rows_per_chunk, world)
+                row_ranges = [tdist.row_range_of_chunks(plan.rows_per_chunk, lo, hi) for lo, hi in ranges]
+                r_lo, r_hi = row_ranges[rank]
+                local = self._engine().compress(q_sets, enc[r_lo:r_hi], ids, query_set=query_set[r_lo:r_hi],
+                                                text_set=None if text_set is None else text_set[r_lo:r_hi],
+                                                out_dtype=dtype)
+                comp = tdist.all_gather_rows(local, [hi - lo for lo, hi in row_ranges], group)
 
         # --- assemble [static, sep, (K compressed, sep) x rows] per chunk (:1668-1692)
         Ls = L

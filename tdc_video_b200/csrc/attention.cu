@@ -45,7 +45,10 @@ struct KVRegs {
   uint4 v[4];  // tokens t0+2c, t0+2c+1, t0+8+2c, t0+8+2c+1 at dh g*8..g*8+7
 };
 
-__global__ void __launch_bounds__(128) tdc_attention_kernel(AttentionArgs a) {
+// kTwoSeg = false: all KV (and Q) tokens of a row are contiguous (cross-attention, text-less
+// self-attention) so the per-token slab-row lookup collapses to base + token.
+template <bool kTwoSeg>
+__global__ void __launch_bounds__(128, 4) tdc_attention_kernel(AttentionArgs a) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2;  // MMA "group" id: fragment row / column owner
   const int c = lane & 3;   // thread within group
@@ -67,8 +70,10 @@ __global__ void __launch_bounds__(128) tdc_attention_kernel(AttentionArgs a) {
   // ---- Q fragments: rows g and g+8 of the block, dh chunks {c*8..+7} and {32+c*8..+7}
   const int qi0 = qb * 16 + g, qi1 = qi0 + 8;
   const int qc0 = qi0 < a.nq ? qi0 : a.nq - 1, qc1 = qi1 < a.nq ? qi1 : a.nq - 1;
-  const long long qrow0 = seg_row(r, qc0, a.q_seg1, a.q_seg2, a.q_base1, a.q_base2);
-  const long long qrow1 = seg_row(r, qc1, a.q_seg1, a.q_seg2, a.q_base1, a.q_base2);
+  const long long qrow0 = kTwoSeg ? seg_row(r, qc0, a.q_seg1, a.q_seg2, a.q_base1, a.q_base2)
+                                  : a.q_base1 + static_cast<long long>(r) * a.q_seg1 + qc0;
+  const long long qrow1 = kTwoSeg ? seg_row(r, qc1, a.q_seg1, a.q_seg2, a.q_base1, a.q_base2)
+                                  : a.q_base1 + static_cast<long long>(r) * a.q_seg1 + qc1;
   uint32_t qa[8], qb_[8];
   {
     const __nv_bfloat16* p0 = a.q + qrow0 * a.ldq + h * 64 + c * 8;
@@ -83,13 +88,21 @@ __global__ void __launch_bounds__(128) tdc_attention_kernel(AttentionArgs a) {
 
   const __nv_bfloat16* kbase = a.k + h * 64 + c * 8;
   const __nv_bfloat16* vbase = a.v + h * 64 + g * 8;
+  if (!kTwoSeg) {  // fold the row's first KV token into the base pointers
+    const long long first = a.kv_base1 + static_cast<long long>(r) * a.kv_seg1;
+    kbase += first * a.ldk;
+    vbase += first * a.ldv;
+  }
+  auto kv_row = [&](int t) -> long long {
+    return kTwoSeg ? seg_row(r, t, a.kv_seg1, a.kv_seg2, a.kv_base1, a.kv_base2) : static_cast<long long>(t);
+  };
   auto load_group = [&](int t0, KVRegs& kv) {
     // clamp to the last valid token: out-of-range columns are masked to P = 0 below
     int tk0 = t0 + g, tk1 = t0 + 8 + g;
     tk0 = tk0 < kvn ? tk0 : kvn - 1;
     tk1 = tk1 < kvn ? tk1 : kvn - 1;
-    const __nv_bfloat16* pk0 = kbase + seg_row(r, tk0, a.kv_seg1, a.kv_seg2, a.kv_base1, a.kv_base2) * a.ldk;
-    const __nv_bfloat16* pk1 = kbase + seg_row(r, tk1, a.kv_seg1, a.kv_seg2, a.kv_base1, a.kv_base2) * a.ldk;
+    const __nv_bfloat16* pk0 = kbase + kv_row(tk0) * a.ldk;
+    const __nv_bfloat16* pk1 = kbase + kv_row(tk1) * a.ldk;
     kv.k[0] = __ldg(reinterpret_cast<const uint4*>(pk0));
     kv.k[1] = __ldg(reinterpret_cast<const uint4*>(pk0 + 32));
     kv.k[2] = __ldg(reinterpret_cast<const uint4*>(pk1));
@@ -98,7 +111,7 @@ __global__ void __launch_bounds__(128) tdc_attention_kernel(AttentionArgs a) {
     for (int j = 0; j < 4; ++j) {
       int tv = t0 + (j >> 1) * 8 + c * 2 + (j & 1);
       tv = tv < kvn ? tv : kvn - 1;
-      const __nv_bfloat16* pv = vbase + seg_row(r, tv, a.kv_seg1, a.kv_seg2, a.kv_base1, a.kv_base2) * a.ldv;
+      const __nv_bfloat16* pv = vbase + kv_row(tv) * a.ldv;
       kv.v[j] = __ldg(reinterpret_cast<const uint4*>(pv));
     }
   };
@@ -220,7 +233,10 @@ int attention_launch(const AttentionArgs& a, cudaStream_t stream, const char** e
     if (err) *err = "attention: grid too large";
     return TDC_EINVAL;
   }
-  tdc_attention_kernel<<<static_cast<unsigned>(blocks), 128, 0, stream>>>(a);
+  if (a.q_seg2 > 0 || a.kv_seg2 > 0)
+    tdc_attention_kernel<true><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(a);
+  else
+    tdc_attention_kernel<false><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(a);
   const cudaError_t rc = cudaGetLastError();
   if (rc != cudaSuccess) {
     if (err) *err = cudaGetErrorString(rc);
