@@ -59,6 +59,16 @@ def flops_per_row(L, d_enc, K, T, d_out):
     return kv + rest, kv
 
 
+def measured_traffic_per_row():
+    """DRAM bytes per row of the KV-projection GEMM from the committed ncu --set full capture
+    (profiles/kv_gemm_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum over the rows of that launch)."""
+    p = os.path.join(ROOT, "profiles", "kv_gemm_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return (d["dram_bytes_read"] + d["dram_bytes_write"]) / d["rows_in_launch"]
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -181,6 +191,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cta-group", type=int, default=0)
+    ap.add_argument("--gather-batches", type=int, default=4, help="row batches per step at N > 1 (comm/compute overlap)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.segments:
@@ -224,14 +235,23 @@ def main():
     query_set = (torch.arange(rows) // (w["frames_per_segment"] - 1)).to(torch.int32)
     enc = enc_host.to(dev)
     q_dev, qs_dev = q_sets.to(dev), query_set.to(dev)
-    gathered = torch.empty((world * rows, K, d_out), dtype=torch.bfloat16, device=dev) if world > 1 else None
+    gathered = torch.empty((world, rows, K, d_out), dtype=torch.bfloat16, device=dev) if world > 1 else None
+    nb = max(1, args.gather_batches)
+    bounds = [(rows * b // nb, rows * (b + 1) // nb) for b in range(nb)]
 
     def step():
-        out = eng.compress(q_dev, enc, query_set=qs_dev, out_dtype=torch.bfloat16)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
-            return gathered
-        return out
+        if world == 1:
+            return eng.compress(q_dev, enc, query_set=qs_dev, out_dtype=torch.bfloat16)
+        # the path's one exchange step: all-gather of the compressed tokens, issued per row batch on
+        # NCCL's stream so that it overlaps the next batch's kernels; every rank ends with the
+        # rank-ordered sequence [world, rows, K, d_out]
+        works = []
+        for r0, r1 in bounds:
+            out = eng.compress(q_dev, enc[r0:r1], query_set=qs_dev[r0:r1], out_dtype=torch.bfloat16)
+            works.append(dist.all_gather([gathered[w, r0:r1] for w in range(world)], out, async_op=True))
+        for wk in works:
+            wk.wait()
+        return gathered.view(world * rows, K, d_out)
 
     def barrier():
         if world > 1:
@@ -257,7 +277,7 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
-    launches = eng.launch_count() - launches0 + (args.steps if world > 1 else 0)
+    launches = eng.launch_count() - launches0   # our kernels only (NCCL's are not counted)
     prof = eng.profile()
     eng.set_profiling(False)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -277,7 +297,7 @@ def main():
         for _ in range(args.e2e_steps):
             eng.compress_host(q_sets, enc_host, out_host, query_set=query_set, rows_per_batch=args.e2e_rows_per_batch)
             if world > 1:
-                dist.all_gather_into_tensor(gathered, out_host.to(dev, non_blocking=True))
+                dist.all_gather_into_tensor(gathered.view(world * rows, K, d_out), out_host.to(dev, non_blocking=True))
         e1.record()
         barrier()
         te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -314,7 +334,12 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"kernel": "tdc_gemm_kernel (cross-attn K/V projection, all 6 layers, N=9216)", "bound": "tensor",
                      "achieved": kv_achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": (kv_achieved / peaks["tflops_sustained"]) if kv_achieved else None, "traffic": None,
+                     "frac": (kv_achieved / peaks["tflops_sustained"]) if kv_achieved else None,
+                     "traffic": (measured_traffic_per_row() * rows * args.steps / max(kv_n, 1))
+                     if measured_traffic_per_row() else None,
+                     "traffic_note": "bytes per launch = ncu dram read+write per row (profiles/kv_gemm_traffic.json) x rows "
+                                     "per launch; algorithmic = rows*L*(d_enc + 9216)*2 B",
+                     "algorithmic_bytes": rows * args.steps / max(kv_n, 1) * L * (d_enc + 2 * H * N_CROSS) * 2,
                      "peak_source": peaks["source"] + " bf16_tflops_sustained", "launches": kv_n,
                      "avg_launch_ms": kv_ms / max(kv_n, 1), "share_of_step": kv_ms / (ms_step * args.steps)},
         "path": {"algorithmic_tflops": path_tflops, "frac_of_sustained_peak": path_tflops / peaks["tflops_sustained"],

@@ -144,6 +144,16 @@ int tdc_gelu_mlp(const void* x, const void* w0, const float* b0, const void* w1,
 int tdc_avg_pool_tokens(const void* frames, int32_t dtype, int32_t n, int32_t tokens, int32_t d, int32_t num_query,
                         void* out_bf16, tdc_stream_t stream);
 
+/* replaces: the similarity + boundary selection of adapt_segment — tdc/cambrian_arch.py:832-849.
+ *   feats [n_frames, dim] (dtype; dim = tokens * channels of the DINO features, flattened)
+ *   cos_out [n_frames - 1] fp32: F.cosine_similarity(frame i, frame i+1)
+ *   boundaries_out [min(max_segments, n_frames - 1)] int64: sort(argsort(cos)[:max_segments])
+ *   workspace: tdc_segment_workspace_bytes(n_frames, dim) bytes */
+size_t tdc_segment_workspace_bytes(int32_t n_frames, int64_t dim);
+int tdc_segment_boundaries(const void* feats, int32_t dtype, int32_t n_frames, int64_t dim, int32_t max_segments,
+                           float* cos_out, int64_t* boundaries_out, void* workspace, size_t workspace_bytes,
+                           tdc_stream_t stream);
+
 /* dtype conversion used by the host wrapper (fp32 / fp16 -> bf16 and back) */
 int tdc_convert(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t count, tdc_stream_t stream);
 

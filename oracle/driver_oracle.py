@@ -30,6 +30,29 @@ import torch.nn.functional as F
 from . import qformer_oracle as qo
 
 
+def adapt_segment(frame_features, max_num_segments: int = 24, window_size: int = 64):
+    """Per-video body of CambrianMetaForCausalLM.adapt_segment (cambrian_arch.py:801-849), fp32 CPU:
+    returns (selected_frame_indices, segment_frame_indices, cos_similarities | None)."""
+    f = qo._t(frame_features)
+    n = len(f)
+    if n <= max_num_segments + 1:                                   # :803-810
+        return torch.arange(n), torch.arange(n), None
+    max_num_frames = 224                                            # :813
+    if n > max_num_frames:                                          # :815-822
+        interval = n / float(max_num_frames)
+        indices = [int(interval * i) for i in range(max_num_frames)]
+    else:
+        indices = list(range(n))
+    q = f[indices].flatten(1, 2) if f.dim() == 3 else f[indices]    # :832
+    prev, nxt = q[:-1], q[1:]
+    sims = []
+    for s0 in range(0, len(prev), window_size):                     # :836-841 (windowing does not change values)
+        sims.append(F.cosine_similarity(prev[s0:s0 + window_size], nxt[s0:s0 + window_size], dim=1))
+    cos = torch.cat(sims)
+    seg, _ = torch.argsort(cos)[:max_num_segments].sort()           # :849
+    return torch.tensor(indices), seg, cos
+
+
 def segment_sizes_from_boundaries(segment_frame_indices, n_frames: int):
     """cambrian_arch.py:1541-1544: boundaries after frames `segment_frame_indices` ->
     frames per segment (empty segments are possible and skipped by the loop, :1604-1605)."""

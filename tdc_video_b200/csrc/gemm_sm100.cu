@@ -192,12 +192,12 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (CG == 1) {
             mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
             tma_load_2d(sa, &map_a, &full_bar[stage], kb * kBlockK, row_a);
-            tma_load_2d(sb, &map_w, &full_bar[stage], kb * kBlockK, row_w);
+            tma_load_2d(sb, &map_w, &full_bar[stage], kb * kBlockK, row_w, kL2EvictLast);
           } else {
             // both CTAs' bytes are credited to the leader's barrier
             if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
             tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * kBlockK, row_a);
-            tma_load_2d_pair(sb, &map_w, &full_bar[stage], kb * kBlockK, row_w);
+            tma_load_2d_pair(sb, &map_w, &full_bar[stage], kb * kBlockK, row_w, kL2EvictLast);  // W: keep in L2
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }

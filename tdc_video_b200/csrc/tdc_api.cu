@@ -649,6 +649,30 @@ int tdc_avg_pool_tokens(const void* frames, int32_t dtype, int32_t n, int32_t to
   return rc;
 }
 
+size_t tdc_segment_workspace_bytes(int32_t n_frames, int64_t dim) {
+  if (n_frames < 2 || dim <= 0) return 0;
+  return static_cast<size_t>(n_frames - 1) * frame_cosine_slices(dim) * 3 * sizeof(float);
+}
+
+int tdc_segment_boundaries(const void* feats, int32_t dtype, int32_t n_frames, int64_t dim, int32_t max_segments,
+                           float* cos_out, int64_t* boundaries_out, void* workspace, size_t workspace_bytes,
+                           tdc_stream_t stream) {
+  if (n_frames < 2) return TDC_OK;
+  if (feats == nullptr || cos_out == nullptr || boundaries_out == nullptr || workspace == nullptr) {
+    g_create_error = "tdc_segment_boundaries: null pointer";
+    return TDC_EINVAL;
+  }
+  if (dtype < TDC_BF16 || dtype > TDC_F32 || max_segments <= 0) { g_create_error = "tdc_segment_boundaries: bad dtype / max_segments"; return TDC_EINVAL; }
+  if (workspace_bytes < tdc_segment_workspace_bytes(n_frames, dim)) { g_create_error = "tdc_segment_boundaries: workspace too small"; return TDC_EWORKSPACE; }
+  const char* err = nullptr;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = frame_cosine_launch(feats, dtype, n_frames, dim, static_cast<float*>(workspace), cos_out, s, &err);
+  if (rc == TDC_OK)
+    rc = select_smallest_launch(cos_out, n_frames - 1, max_segments, reinterpret_cast<long long*>(boundaries_out), s, &err);
+  if (rc != TDC_OK) g_create_error = err ? err : "tdc_segment_boundaries failed";
+  return rc;
+}
+
 int tdc_convert(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t count, tdc_stream_t stream) {
   const char* err = nullptr;
   const int rc = convert_launch(src, src_dtype, dst, dst_dtype, count, static_cast<cudaStream_t>(stream), &err);

@@ -78,4 +78,12 @@ int take_query_tokens_launch(const void* hidden, int dtype, int rows, int tokens
 int avg_pool_tokens_launch(const void* frames, int dtype, int n, int tokens, int d, int num_query,
                            __nv_bfloat16* out, cudaStream_t stream, const char** err);
 
+// Adaptive segmentation (tdc/cambrian_arch.py:832-849): cos[i] = cosine_similarity(frame i, frame i+1) over
+// the flattened feature dim; partial_ws holds (n_frames-1) * frame_cosine_slices(dim) * 3 floats.
+inline int frame_cosine_slices(long long dim) { return dim >= (1 << 16) ? 8 : 1; }
+int frame_cosine_launch(const void* feats, int dtype, int n_frames, long long dim, float* partial_ws, float* cos,
+                        cudaStream_t stream, const char** err);
+// out[0..min(k,n)) = indices of the k smallest x, ascending by index (== sort(argsort(x)[:k]))
+int select_smallest_launch(const float* x, int n, int k, long long* out, cudaStream_t stream, const char** err);
+
 }  // namespace tdc

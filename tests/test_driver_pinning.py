@@ -66,3 +66,22 @@ def test_driver_oracle_equals_real_reference_function(n_frames, query_type, text
     off, tok, _ = output_layout(plan, 156, K, add_static)
     keep = truncation_keep_index(off, tok, max_visual_len)
     assert (int(tok.sum()) if keep is None else len(keep)) == got.shape[0]
+
+
+@pytest.mark.parametrize("n_frames", [12, 26, 60, 300])
+def test_adapt_segment_oracle_equals_reference(n_frames):
+    """oracle.adapt_segment vs the reference method itself (called on the harness object)."""
+    from oracle import harness
+    arch = harness._load_cambrian_arch()
+    rs = np.random.RandomState(n_frames)
+    dino = torch.from_numpy(_tables(n_frames, n_frames)[1])
+    imgs = torch.zeros(n_frames, 1)
+
+    class Bare(arch.CambrianMetaForCausalLM):
+        def get_model(self):
+            return None
+
+    feats, split, _, sel_all, seg_all = Bare().adapt_segment(dino, [n_frames], [imgs, imgs], max_num_segments=24)
+    sel, seg, cos = driver_oracle.adapt_segment(dino, 24)
+    assert torch.equal(sel, sel_all[0]) and torch.equal(seg, seg_all[0])
+    assert split == [len(sel)] and feats.shape[0] == len(sel)

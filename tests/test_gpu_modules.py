@@ -144,3 +144,30 @@ def test_avg_pool_tokens_matches_adaptive_avg_pool1d():
     got = avg_pool_tokens(x, 16).float().cpu()
     ref = oracle.avg_pool_queries(x.cpu(), 16)
     assert torch.allclose(got, ref, atol=1e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("n_frames,dtype", [(12, torch.bfloat16), (60, torch.bfloat16), (224, torch.float16),
+                                            (300, torch.float32)])
+def test_adapt_segment_matches_oracle(n_frames, dtype):
+    """tdc_segment_boundaries vs the restated adapt_segment (cambrian_arch.py:783-861): identical boundary
+    indices, cosine similarities within 1e-3 (features drift slowly with a few well-separated jumps)."""
+    from tdc_video_b200.segment import adapt_segment, segment_sizes
+    rs = np.random.RandomState(n_frames)
+    dino = np.cumsum(rs.standard_normal((n_frames, 1, 64)) * 0.05, axis=0) + rs.standard_normal((1, 576, 64))
+    jumps = rs.choice(np.arange(1, n_frames), size=min(24, max(1, n_frames // 6)), replace=False)
+    dino[jumps] += rs.standard_normal((len(jumps), 1, 64)) * np.linspace(1.0, 4.0, len(jumps))[:, None, None]
+    feats = torch.from_numpy(dino.astype(np.float32)).to(dtype)
+    sel, seg, cos = adapt_segment(feats.cuda(), 24)
+    sel_o, seg_o, cos_o = driver_oracle.adapt_segment(feats.float(), 24)
+    assert torch.equal(sel, sel_o)
+    if cos_o is None:
+        assert cos is None and torch.equal(seg.cpu(), seg_o)
+    else:
+        assert torch.allclose(cos.cpu(), cos_o, atol=1e-3)
+        # the 24 chosen similarities must be separated from the rest by more than the tolerance for the
+        # index comparison to be meaningful
+        srt = torch.sort(cos_o).values
+        if len(srt) > 24:
+            assert float(srt[24] - srt[23]) > 2e-3
+        assert torch.equal(seg.cpu(), seg_o)
+    assert sum(segment_sizes(seg, len(sel))) == len(sel)

@@ -129,3 +129,58 @@ def test_errors_are_loud():
     with pytest.raises(TdcError, match="input_ids|text"):
         eng.forward(q, enc, torch.zeros(1, 3, dtype=torch.long, device="cuda"))
     assert eng.forward(q[:0], enc[:0]).shape == (0, 4, 64)
+
+
+# ---- wider shapes: BASELINE configs 1/5 (segment-level KV, K=64 sweep), long prompts, fp16 I/O ----------
+@pytest.mark.parametrize("K,L,T,d_enc,rows,dtype", [
+    (64, 626, 0, 1152, 5, torch.bfloat16),     # config 5 query sweep on the north-star "segment KV" layout
+    (16, 1000, 0, 1152, 4, torch.bfloat16),    # ~10^3 KV tokens per row
+    (16, 206, 40, 3072, 5, torch.bfloat16),    # Llama-3.2-3B widths with a 40-token prompt
+    (32, 156, 0, 3584, 6, torch.float16),      # reference inference dtype (fp16, builder.py:69)
+    (16, 17, 256, 1152, 3, torch.bfloat16),    # max_length=256 prompt (cambrian_arch.py:1536), tiny KV
+])
+def test_wide_shapes_vs_oracle(K, L, T, d_enc, rows, dtype):
+    geom = QFormerGeometry(d_enc=d_enc, d_out=3072, vocab=30522 if T else 0)
+    sd = make_state_dict(geom, 50 + K + T, stress=2.0, with_text=T > 0)
+    inp = make_inputs(geom, 60 + K, rows=rows, kv_tokens=L, num_query=K, num_text=T, audio_tokens=min(50, L // 3))
+    eng = _engine(geom, sd)
+    q = torch.from_numpy(inp["query_embeds"]).cuda().to(dtype)
+    enc = torch.from_numpy(inp["enc"]).cuda().to(dtype)
+    ids = None if T == 0 else torch.from_numpy(inp["input_ids"]).cuda()
+    hidden = eng.forward(q, enc, ids)
+    comp = eng.compress(q, enc, ids)
+    torch.cuda.synchronize()
+    assert hidden.dtype == dtype and comp.dtype == dtype
+    ref_h = oracle.qformer_forward(sd, geom, q.float().cpu(), enc.float().cpu(), None if ids is None else ids.cpu())
+    _check(hidden, ref_h, f"wide K={K} L={L} T={T}/hidden")
+    _check(comp, oracle.proj_norm(sd, ref_h, K), f"wide K={K} L={L} T={T}/compressed")
+
+
+def test_properties_at_scale():
+    """1200 rows at the bench geometry (Qwen2-7B widths, L=206): size-independent properties —
+    unit-norm tokens, row-permutation equivariance (bit exact: rows are independent), per-row ragged
+    kv_len equals truncating that row — plus a sampled comparison with the oracle."""
+    geom = QFormerGeometry(d_enc=3584, d_out=3584, vocab=0)
+    sd = make_state_dict(geom, 77, with_text=False)
+    eng = _engine(geom, sd)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    R, L, K = 1200, 206, 16
+    enc = torch.randn((R, L, 3584), generator=g, device="cuda").bfloat16()
+    qsets = torch.randn((R // 3, K, 768), generator=g, device="cuda")
+    qmap = (torch.arange(R) // 3).int()
+    out = eng.compress(qsets, enc, query_set=qmap)
+    norms = out.float().norm(dim=-1)
+    assert torch.allclose(norms, torch.ones_like(norms), atol=4e-3)
+    perm = torch.randperm(R, generator=torch.Generator().manual_seed(1))
+    out_p = eng.compress(qsets, enc[perm.cuda()], query_set=qmap[perm])
+    assert torch.equal(out_p, out[perm.cuda()])
+    kv = torch.full((R,), L, dtype=torch.int32)
+    kv[::7] = 97
+    out_kv = eng.compress(qsets, enc, query_set=qmap, kv_len=kv)
+    short = eng.compress(qsets, enc[::7, :97].contiguous(), query_set=qmap[::7])
+    assert torch.equal(out_kv[::7], short)
+    keep = torch.ones(R, dtype=torch.bool); keep[::7] = False
+    assert torch.equal(out_kv[keep.cuda()], out[keep.cuda()])
+    idx = torch.tensor([0, 1, 599, 600, 1198, 1199])
+    ref = oracle.compress(sd, geom, qsets[qmap[idx].long()].cpu(), enc[idx.cuda()].float().cpu())
+    _check(out[idx.cuda()], ref, "scale/sampled rows")
