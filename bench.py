@@ -191,7 +191,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cta-group", type=int, default=0)
-    ap.add_argument("--gather-batches", type=int, default=4, help="row batches per step at N > 1 (comm/compute overlap)")
+    ap.add_argument("--gather-batches", type=int, default=2, help="row batches per step at N > 1 (comm/compute overlap)")
+    ap.add_argument("--no-multicast", action="store_true", help="N > 1: use the NCCL all-gather instead of multicast stores")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.segments:
@@ -238,6 +239,19 @@ def main():
     gathered = torch.empty((world, rows, K, d_out), dtype=torch.bfloat16, device=dev) if world > 1 else None
     nb = max(1, args.gather_batches)
     bounds = [(rows * b // nb, rows * (b + 1) // nb) for b in range(nb)]
+    mcast, exchange = None, "none (1 GPU)"
+    if world > 1:
+        exchange = "NCCL all-gather of compressed tokens"
+        if not args.no_multicast:
+            try:
+                from tdc_video_b200.dist import MulticastGather
+                mcast = MulticastGather(rows, (K, d_out), torch.bfloat16, dev)
+                exchange = "NVSwitch multicast stores (multimem.st) from the final kernel + device barrier"
+            except Exception as e:  # transport fallback only; compute path is identical
+                if rank == 0:
+                    print(f"[bench] symmetric-memory multicast unavailable ({type(e).__name__}: {e}); using NCCL",
+                          file=sys.stderr)
+                mcast = None
 
     def step():
         if world == 1:
@@ -245,6 +259,14 @@ def main():
         # the path's one exchange step: all-gather of the compressed tokens, issued per row batch on
         # NCCL's stream so that it overlaps the next batch's kernels; every rank ends with the
         # rank-ordered sequence [world, rows, K, d_out]
+        if mcast is not None:
+            # all-gather fused into the producing kernel: the L2-normalise kernel stores every row through
+            # the multicast mapping, so all ranks receive it while the kernel runs
+            for r0, r1 in bounds:
+                eng.compress_multicast(q_dev, enc[r0:r1], mcast.slot_ptr(r0), query_set=qs_dev[r0:r1],
+                                       out_dtype=torch.bfloat16)
+            mcast.barrier()
+            return mcast.gathered
         works = []
         for r0, r1 in bounds:
             out = eng.compress(q_dev, enc[r0:r1], query_set=qs_dev[r0:r1], out_dtype=torch.bfloat16)
@@ -298,6 +320,7 @@ def main():
             eng.compress_host(q_sets, enc_host, out_host, query_set=query_set, rows_per_batch=args.e2e_rows_per_batch)
             if world > 1:
                 dist.all_gather_into_tensor(gathered.view(world * rows, K, d_out), out_host.to(dev, non_blocking=True))
+                # (e2e keeps the plain NCCL exchange: the result is read back to the host per batch anyway)
         e1.record()
         barrier()
         te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -325,8 +348,7 @@ def main():
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["label"], "segments_per_gpu": S, "rows_per_gpu": rows,
                    "kv_tokens": L, "d_enc": d_enc, "d_out": d_out, "num_query": K, "num_text": 0,
-                   "parallelism": f"dp{world} (video-second ranges per GPU" + (", NCCL all-gather of compressed tokens)"
-                                                                                if world > 1 else ")"),
+                   "parallelism": f"dp{world} (video-second ranges per GPU)", "exchange": exchange,
                    "l2": f"inputs {enc.numel() * 2 / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
                    "accumulate": "fp32 (TMEM), LN/softmax/residual fp32"},
         "clocks": clocks,

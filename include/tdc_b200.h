@@ -126,6 +126,17 @@ int tdc_compress(tdc_handle* h, const void* query_embeds, int32_t query_dtype, c
                  const int32_t* kv_len, int32_t rows, int32_t kv_tokens, int32_t num_query, int32_t num_text,
                  void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes, tdc_stream_t stream);
 
+/* tdc_compress whose result is written through an NVSwitch MULTICAST address (multimem.st): `out_multicast`
+ * is this rank's slot inside a symmetric buffer mapped with a multicast VA (e.g. torch symmetric memory's
+ * multicast_ptr + rank offset), so the final L2-normalise kernel delivers every row to all GPUs of the group
+ * at once — the path's only exchange step (all-gather of the compressed tokens) fused into
+ * the producing kernel.  The caller synchronises the group (barrier) before reading peers' rows. */
+int tdc_compress_multicast(tdc_handle* h, const void* query_embeds, int32_t query_dtype, const int32_t* query_set,
+                           const int64_t* input_ids, const int32_t* text_set, const void* enc, int32_t enc_dtype,
+                           const int32_t* kv_len, int32_t rows, int32_t kv_tokens, int32_t num_query,
+                           int32_t num_text, void* out_multicast, int32_t out_dtype, void* workspace,
+                           size_t workspace_bytes, tdc_stream_t stream);
+
 /* ---- small dense helpers on the same path ---------------------------------------- */
 /* replaces: nn.Linear forward — query_proj / audio_proj / vision_proj as plain callables
  * (cambrian_arch.py:1613,1638,1665).  y[m, n] = x[m, k] . w[n, k]^T + bias.

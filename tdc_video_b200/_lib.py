@@ -24,7 +24,7 @@ KERNEL_CLASS_NAMES = ["kv_gemm", "query_gemm", "attention", "rowops"]
 # every symbol include/tdc_b200.h declares (checked by tests/test_c_abi.py)
 EXPORTED_SYMBOLS = [
     "tdc_abi_version", "tdc_create", "tdc_destroy", "tdc_last_error", "tdc_load_weights", "tdc_workspace_bytes",
-    "tdc_qformer_forward", "tdc_proj_norm", "tdc_compress", "tdc_linear", "tdc_gelu_mlp", "tdc_avg_pool_tokens",
+    "tdc_qformer_forward", "tdc_proj_norm", "tdc_compress", "tdc_compress_multicast", "tdc_linear", "tdc_gelu_mlp", "tdc_avg_pool_tokens",
     "tdc_convert", "tdc_segment_workspace_bytes", "tdc_segment_boundaries", "tdc_set_profiling", "tdc_get_profile", "tdc_reset_profile", "tdc_launch_count",
 ]
 
@@ -58,6 +58,8 @@ def _declare(lib: C.CDLL) -> None:
     fwd = [vp, vp, i32, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp, sz, vp]
     lib.tdc_qformer_forward.argtypes = fwd
     lib.tdc_compress.argtypes = fwd
+    lib.tdc_compress_multicast.argtypes = fwd
+    lib.tdc_compress_multicast.restype = C.c_int
     lib.tdc_proj_norm.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp, sz, vp]
     lib.tdc_linear.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.tdc_gelu_mlp.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]

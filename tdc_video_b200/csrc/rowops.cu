@@ -168,10 +168,23 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
   for (int j = lane; j < hidden / 4; j += 32) store4_from_f32(out, out_dtype, tok * (hidden / 4) + j, s[j]);
 }
 
+// 16-byte store; kMulticast: `p` is an NVSwitch multicast address (all GPUs of the group receive the
+// bytes with one store — the all-gather of the compressed tokens rides on this kernel's output).
+template <bool kMulticast>
+__device__ __forceinline__ void store16(void* p, uint4 v) {
+  if (kMulticast)
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+  else
+    *reinterpret_cast<uint4*>(p) = v;
+}
+
+template <bool kMulticast>
 __global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restrict__ x, long long ldx,
                                                            void* __restrict__ out, int out_dtype, long long rows,
                                                            int width) {
-  // one 256-thread block per row (width is the LLM hidden size, 3-4 K)
+  // one 256-thread block per row (width is the LLM hidden size, 3-4 K); 8 elements per thread step
   __shared__ float red[8];
   const long long row = blockIdx.x;
   const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
@@ -187,10 +200,27 @@ __global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restri
 #pragma unroll
   for (int i = 0; i < 8; ++i) tot += red[i];
   const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);  // F.normalize: x / max(||x||, eps)
-  for (int j = threadIdx.x; j < width / 4; j += 256) {
-    float4 v = xr[j];
-    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
-    store4_from_f32(out, out_dtype, row * (width / 4) + j, v);
+  uint8_t* orow = static_cast<uint8_t*>(out) + row * width * (out_dtype == TDC_F32 ? 4 : 2);
+  for (int j = threadIdx.x; j < width / 8; j += 256) {
+    float4 a = xr[2 * j], b = xr[2 * j + 1];
+    a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+    b.x *= inv; b.y *= inv; b.z *= inv; b.w *= inv;
+    if (out_dtype == TDC_F32) {
+      store16<kMulticast>(orow + j * 32, *reinterpret_cast<uint4*>(&a));
+      store16<kMulticast>(orow + j * 32 + 16, *reinterpret_cast<uint4*>(&b));
+    } else {
+      uint4 pk;
+      if (out_dtype == TDC_BF16) {
+        pk.x = pack_bf16x2(a.x, a.y); pk.y = pack_bf16x2(a.z, a.w);
+        pk.z = pack_bf16x2(b.x, b.y); pk.w = pack_bf16x2(b.z, b.w);
+      } else {
+        const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+        const __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+        pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
+      }
+      store16<kMulticast>(orow + j * 16, pk);
+    }
   }
 }
 
@@ -276,13 +306,16 @@ int gather_rows_launch(const float* h_f32, int hidden, int rows, int num_query, 
 }
 
 int l2_normalize_launch(const float* x, long long ldx, void* out, int out_dtype, long long rows, int width,
-                        cudaStream_t stream, const char** err) {
+                        bool multicast, cudaStream_t stream, const char** err) {
   if (rows <= 0) return TDC_OK;
-  if (width % 4 != 0 || ldx % 4 != 0) {
-    if (err) *err = "l2_normalize: width must be a multiple of 4";
+  if (width % 8 != 0 || ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(out) & 15)) {
+    if (err) *err = "l2_normalize: width must be a multiple of 8 and the output 16-byte aligned";
     return TDC_EINVAL;
   }
-  l2_normalize_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(x, ldx, out, out_dtype, rows, width);
+  if (multicast)
+    l2_normalize_kernel<true><<<static_cast<unsigned>(rows), 256, 0, stream>>>(x, ldx, out, out_dtype, rows, width);
+  else
+    l2_normalize_kernel<false><<<static_cast<unsigned>(rows), 256, 0, stream>>>(x, ldx, out, out_dtype, rows, width);
   return check_launch(err);
 }
 

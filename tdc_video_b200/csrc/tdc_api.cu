@@ -289,6 +289,7 @@ struct ForwardCall {
   long long rows; int L, K, T;
   void* out; int out_dtype;   // hidden [rows, K+T, H] or compressed [rows, K, d_out]
   bool compress;
+  bool multicast = false;     // compress only: `out` is an NVSwitch multicast address
 };
 
 #define TDC_TRY(expr)                                         \
@@ -424,7 +425,7 @@ int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long
     const size_t osz = f.out_dtype == TDC_F32 ? 4 : 2;
     void* out = static_cast<uint8_t*>(f.out) + static_cast<size_t>(row0) * K * c.d_out * osz;
     KernelScope ks(h, TDC_K_ROWOPS, s);
-    TDC_TRY(l2_normalize_launch(w.proj, c.d_out, out, f.out_dtype, MQ, c.d_out, s, &err));
+    TDC_TRY(l2_normalize_launch(w.proj, c.d_out, out, f.out_dtype, MQ, c.d_out, f.multicast, s, &err));
   }
   return TDC_OK;
 }
@@ -587,6 +588,18 @@ int tdc_compress(tdc_handle* h, const void* query_embeds, int32_t query_dtype, c
   return run_call(h, f, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int tdc_compress_multicast(tdc_handle* h, const void* query_embeds, int32_t query_dtype, const int32_t* query_set,
+                           const int64_t* input_ids, const int32_t* text_set, const void* enc, int32_t enc_dtype,
+                           const int32_t* kv_len, int32_t rows, int32_t kv_tokens, int32_t num_query,
+                           int32_t num_text, void* out_multicast, int32_t out_dtype, void* workspace,
+                           size_t workspace_bytes, tdc_stream_t stream) {
+  if (h == nullptr) return TDC_EINVAL;
+  ForwardCall f{query_embeds, query_dtype, query_set, input_ids, text_set, enc, enc_dtype, kv_len,
+                rows, kv_tokens, num_query, num_text, out_multicast, out_dtype, true};
+  f.multicast = true;
+  return run_call(h, f, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int tdc_proj_norm(tdc_handle* h, const void* hidden, int32_t hidden_dtype, int32_t rows, int32_t tokens_per_row,
                   int32_t num_query, void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes,
                   tdc_stream_t stream) {
@@ -610,7 +623,7 @@ int tdc_proj_norm(tdc_handle* h, const void* hidden, int32_t hidden_dtype, int32
   TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, x, c.hidden, h->w_vp, c.hidden, h->b_vp, y, c.d_out, M, c.d_out, c.hidden,
                EPI_BIAS_F32, &err));
   KernelScope ks(h, TDC_K_ROWOPS, s);
-  TDC_TRY(l2_normalize_launch(y, c.d_out, out, out_dtype, M, c.d_out, s, &err));
+  TDC_TRY(l2_normalize_launch(y, c.d_out, out, out_dtype, M, c.d_out, false, s, &err));
   return TDC_OK;
 }
 

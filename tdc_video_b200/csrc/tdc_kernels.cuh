@@ -63,8 +63,9 @@ int gather_rows_launch(const float* h_f32, int hidden, int rows, int num_query, 
                        void* out, int out_dtype, cudaStream_t stream, const char** err);
 
 // F.normalize(x, dim=-1) (eps 1e-12; tdc/cambrian_arch.py:1664-1667): x fp32 [rows, width] -> out_dtype.
+// multicast: `out` is an NVSwitch multicast address (multimem.st): every GPU of the group gets the rows.
 int l2_normalize_launch(const float* x, long long ldx, void* out, int out_dtype, long long rows, int width,
-                        cudaStream_t stream, const char** err);
+                        bool multicast, cudaStream_t stream, const char** err);
 
 // Elementwise dtype conversion.
 int convert_launch(const void* src, int src_dtype, void* dst, int dst_dtype, long long count, cudaStream_t stream,

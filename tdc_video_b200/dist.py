@@ -62,3 +62,37 @@ def all_gather_rows(local: torch.Tensor, rows_per_rank: Sequence[int], group: Op
         return out
     out = out.view((world, rmax) + tail)
     return torch.cat([out[r, : int(n)] for r, n in enumerate(rows_per_rank)], dim=0)
+
+
+class MulticastGather:
+    """Rank-ordered gather buffer `[world, rows, ...]` in torch symmetric memory with an NVSwitch
+    multicast mapping.  Each rank's final kernel stores its rows through `slot_ptr()` (a multicast
+    address), which delivers them into the same slot of EVERY rank's buffer — the all-gather is fused
+    into the producing kernel instead of being a separate NCCL collective.  `barrier()` (device-side,
+    stream-ordered) makes the peers' rows visible before `gathered` is read.
+
+    Raises RuntimeError when symmetric memory / multicast is unavailable (callers fall back to the
+    NCCL all-gather of `all_gather_rows`)."""
+
+    def __init__(self, rows: int, tail: Sequence[int], dtype: torch.dtype, device, group: Optional[dist.ProcessGroup] = None):
+        import torch.distributed._symmetric_memory as symm
+
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.rows, self.tail = int(rows), tuple(int(t) for t in tail)
+        self.buf = symm.empty((self.world, self.rows) + self.tail, dtype=dtype, device=device)
+        self.handle = symm.rendezvous(self.buf, group.group_name)
+        if not getattr(self.handle, "multicast_ptr", 0):
+            raise RuntimeError("symmetric memory has no multicast mapping on this system")
+        self.row_bytes = self.buf[0, 0].numel() * self.buf.element_size() if self.rows else 0
+
+    def slot_ptr(self, row0: int = 0) -> int:
+        """Multicast address of row `row0` of this rank's slot."""
+        return int(self.handle.multicast_ptr) + (self.rank * self.rows + int(row0)) * self.row_bytes
+
+    def barrier(self) -> None:
+        self.handle.barrier()
+
+    @property
+    def gathered(self) -> torch.Tensor:
+        return self.buf.view((self.world * self.rows,) + self.tail)

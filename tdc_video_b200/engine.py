@@ -100,7 +100,7 @@ class QFormerEngine:
 
     # -- the hot path ---------------------------------------------------------------------
     def _run(self, fn, what, query_embeds, enc, input_ids, query_set, text_set, kv_len, out_width, out_tokens,
-             out_dtype):
+             out_dtype, out_ptr=None):
         if enc.dim() != 3 or query_embeds.dim() != 3:
             raise ValueError("query_embeds must be [sets, K, hidden] and enc [rows, L, d_enc]")
         rows, L, d_enc = enc.shape
@@ -121,13 +121,17 @@ class QFormerEngine:
         ts = None if text_set is None else text_set.to(dev, torch.int32).contiguous()
         kl = None if kv_len is None else kv_len.to(dev, torch.int32).contiguous()
         out_dtype = out_dtype or enc.dtype
-        out = torch.empty((rows, out_tokens(K, T), out_width), dtype=out_dtype, device=dev)
+        if out_ptr is None:
+            out = torch.empty((rows, out_tokens(K, T), out_width), dtype=out_dtype, device=dev)
+            dst = _ptr(out)
+        else:  # caller-owned destination (e.g. a multicast address): nothing to return
+            out, dst = None, C.c_void_p(int(out_ptr))
         if rows == 0:
             return out
         ws = self._workspace(rows, L, K, T)
         with torch.cuda.device(dev):
             rc = fn(self._h, _ptr(query_embeds), _dt(query_embeds), _ptr(qs), _ptr(ids), _ptr(ts), _ptr(enc), _dt(enc),
-                    _ptr(kl), rows, L, K, T, _ptr(out), _dt(out), _ptr(ws), ws.numel(), _stream(dev))
+                    _ptr(kl), rows, L, K, T, dst, _DTYPES[out_dtype], _ptr(ws), ws.numel(), _stream(dev))
         check(rc, self._h, what)
         return out
 
@@ -144,6 +148,16 @@ class QFormerEngine:
             raise RuntimeError("engine was created without d_out: no vision_proj")
         return self._run(self.lib.tdc_compress, "tdc_compress", query_embeds, enc, input_ids, query_set, text_set,
                          kv_len, self.cfg.d_out, lambda K, T: K, out_dtype)
+
+    def compress_multicast(self, query_embeds, enc, multicast_ptr: int, input_ids=None, *, query_set=None,
+                           text_set=None, kv_len=None, out_dtype=torch.bfloat16) -> None:
+        """`compress` whose [rows, K, d_out] result is stored through an NVSwitch multicast address
+        (tdc_compress_multicast): every GPU mapped behind `multicast_ptr` receives the rows.  The
+        caller synchronises the group before reading (see dist.MulticastGather)."""
+        if self.cfg.d_out <= 0:
+            raise RuntimeError("engine was created without d_out: no vision_proj")
+        self._run(self.lib.tdc_compress_multicast, "tdc_compress_multicast", query_embeds, enc, input_ids, query_set,
+                  text_set, kv_len, self.cfg.d_out, lambda K, T: K, out_dtype, out_ptr=multicast_ptr)
 
     def compress_host(self, query_embeds: torch.Tensor, enc_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
                       *, query_set: Optional[torch.Tensor] = None, input_ids: Optional[torch.Tensor] = None,
