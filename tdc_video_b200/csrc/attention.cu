@@ -8,15 +8,17 @@
 //
 // This op is bandwidth-bound (16 queries re-use each K/V byte only 16x), so the design is
 // about reading K/V exactly once at full sector efficiency, not about tensor throughput:
-//   * one warp per (row, 16-query block, head); no shared memory, no block-level sync;
-//   * K/V fragments go global -> registers directly in mma.sync operand order.  The
+//   * one warp per (row, 16-query block, head); no block-level sync;
+//   * K/V fragments are fetched directly in mma.sync operand order.  The
 //     contraction index of an MMA may be permuted freely as long as both operands agree,
 //     so each thread fetches 16-byte chunks (a full 32 B sector per thread pair) and the
 //     permutation is absorbed into which 16 B of Q the thread holds (for S = Q K^T) and
 //     into which 16 output columns it owns (for O = P V);
 //   * online softmax in fp32 (exp2 with the 1/sqrt(d)*log2(e) scale folded in), P rounded
 //     to bf16 only as the MMA operand, O accumulated in fp32;
-//   * the next 16-token group's K/V are in flight while the current one is consumed.
+//   * K/V stream through a per-warp cp.async ring in shared memory (3 stages x 4 KB, every thread
+//     writes and later reads only its own 16-byte slots, so no barrier is needed): two 16-token
+//     groups are in flight per warp at zero register cost, 16 warps/SM -> 128 KB in flight per SM.
 // mma.sync m16n8k16 (legacy HMMA path) is deliberate: a 16-row tile is 1/8 of the
 // smallest tcgen05 tile and the kernel sits on the HBM roofline, not the tensor roofline.
 #include "tdc_kernels.cuh"
@@ -39,6 +41,16 @@ __device__ __forceinline__ long long seg_row(int r, int i, int seg1, int seg2, l
   return (i < seg1) ? base1 + static_cast<long long>(r) * seg1 + i
                     : base2 + static_cast<long long>(r) * seg2 + (i - seg1);
 }
+
+constexpr int kStages = 3;            // cp.async ring depth per warp
+constexpr int kSlotsPerStage = 8 * 32;  // 8 x 16-byte chunks per lane
+
+__device__ __forceinline__ void cp_async_16(uint4* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct KVRegs {
   uint4 k[4];  // [tile 0: dh c*8.., dh 32+c*8..] [tile 1: same]
@@ -96,23 +108,26 @@ __global__ void __launch_bounds__(128, 4) tdc_attention_kernel(AttentionArgs a) 
   auto kv_row = [&](int t) -> long long {
     return kTwoSeg ? seg_row(r, t, a.kv_seg1, a.kv_seg2, a.kv_base1, a.kv_base2) : static_cast<long long>(t);
   };
-  auto load_group = [&](int t0, KVRegs& kv) {
+  extern __shared__ uint4 kv_ring[];  // [4 warps][kStages][8 chunks][32 lanes]
+  uint4* ring = kv_ring + (threadIdx.x >> 5) * (kStages * kSlotsPerStage) + lane;
+  // queue the 8 x 16 B this thread needs from token group t0 into ring stage `stage`
+  auto issue_group = [&](int t0, int stage) {
     // clamp to the last valid token: out-of-range columns are masked to P = 0 below
     int tk0 = t0 + g, tk1 = t0 + 8 + g;
     tk0 = tk0 < kvn ? tk0 : kvn - 1;
     tk1 = tk1 < kvn ? tk1 : kvn - 1;
     const __nv_bfloat16* pk0 = kbase + kv_row(tk0) * a.ldk;
     const __nv_bfloat16* pk1 = kbase + kv_row(tk1) * a.ldk;
-    kv.k[0] = __ldg(reinterpret_cast<const uint4*>(pk0));
-    kv.k[1] = __ldg(reinterpret_cast<const uint4*>(pk0 + 32));
-    kv.k[2] = __ldg(reinterpret_cast<const uint4*>(pk1));
-    kv.k[3] = __ldg(reinterpret_cast<const uint4*>(pk1 + 32));
+    uint4* dst = ring + stage * kSlotsPerStage;
+    cp_async_16(dst + 0 * 32, pk0);
+    cp_async_16(dst + 1 * 32, pk0 + 32);
+    cp_async_16(dst + 2 * 32, pk1);
+    cp_async_16(dst + 3 * 32, pk1 + 32);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int tv = t0 + (j >> 1) * 8 + c * 2 + (j & 1);
       tv = tv < kvn ? tv : kvn - 1;
-      const __nv_bfloat16* pv = vbase + kv_row(tv) * a.ldv;
-      kv.v[j] = __ldg(reinterpret_cast<const uint4*>(pv));
+      cp_async_16(dst + (4 + j) * 32, vbase + kv_row(tv) * a.ldv);
     }
   };
 
@@ -121,10 +136,26 @@ __global__ void __launch_bounds__(128, 4) tdc_attention_kernel(AttentionArgs a) 
   for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-  KVRegs cur, nxt;
-  load_group(0, cur);
-  for (int t0 = 0; t0 < kvn; t0 += 16) {
-    if (t0 + 16 < kvn) load_group(t0 + 16, nxt);
+  const int ngroups = (kvn + 15) >> 4;
+#pragma unroll
+  for (int st = 0; st < kStages - 1; ++st) {  // prologue: fill all but one stage
+    if (st < ngroups) issue_group(st * 16, st);
+    cp_async_commit();                        // (empty groups keep the wait count uniform)
+  }
+  for (int gi = 0; gi < ngroups; ++gi) {
+    const int t0 = gi * 16;
+    {
+      const int gn = gi + kStages - 1;        // refill the stage consumed in the previous iteration
+      if (gn < ngroups) issue_group(gn * 16, gn % kStages);
+      cp_async_commit();
+    }
+    cp_async_wait<kStages - 1>();             // group gi has landed (this thread's own slots only)
+    KVRegs cur;
+    {
+      const uint4* src = ring + (gi % kStages) * kSlotsPerStage;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { cur.k[j] = src[j * 32]; cur.v[j] = src[(4 + j) * 32]; }
+    }
 
     // ---- S = Q K^T for 16 tokens: two n-tiles of 8, four k-steps of 16 over dh
     float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
@@ -183,7 +214,6 @@ __global__ void __launch_bounds__(128, 4) tdc_attention_kernel(AttentionArgs a) 
         mma_bf16_16816(o[i], pa0, pa1, pa2, pa3, b0, b1);
       }
     }
-    cur = nxt;
   }
 
   // ---- finalise: row sums across the 4 threads of a group, normalise, store
@@ -233,10 +263,17 @@ int attention_launch(const AttentionArgs& a, cudaStream_t stream, const char** e
     if (err) *err = "attention: grid too large";
     return TDC_EINVAL;
   }
+  constexpr int kSmem = 4 * kStages * kSlotsPerStage * 16;  // 48 KB per 4-warp block -> 4 blocks / SM
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tdc_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(tdc_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    attr_set = true;
+  }
   if (a.q_seg2 > 0 || a.kv_seg2 > 0)
-    tdc_attention_kernel<true><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(a);
+    tdc_attention_kernel<true><<<static_cast<unsigned>(blocks), 128, kSmem, stream>>>(a);
   else
-    tdc_attention_kernel<false><<<static_cast<unsigned>(blocks), 128, 0, stream>>>(a);
+    tdc_attention_kernel<false><<<static_cast<unsigned>(blocks), 128, kSmem, stream>>>(a);
   const cudaError_t rc = cudaGetLastError();
   if (rc != cudaSuccess) {
     if (err) *err = cudaGetErrorString(rc);
