@@ -28,6 +28,8 @@
 #include "tdc_ptx.cuh"
 #include "tdc_b200.h"
 
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 namespace tdc {
@@ -46,6 +48,8 @@ constexpr int kStoreBufs = 2;              // per epilogue warp
 struct EpilogueArgs {
   const float* bias;
   int mode;
+  int slab_cols;  // output columns per slab (== N for a plain matrix)
+  unsigned long long hint_a, hint_w, hint_c;  // L2 eviction policies of the A / W loads and the C stores
 };
 
 template <int CG, int BLOCK_N, int STAGES>
@@ -191,13 +195,13 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           uint8_t* sb = sa + L::kABytes;
           if (CG == 1) {
             mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-            tma_load_2d(sa, &map_a, &full_bar[stage], kb * kBlockK, row_a);
-            tma_load_2d(sb, &map_w, &full_bar[stage], kb * kBlockK, row_w, kL2EvictLast);
+            tma_load_2d(sa, &map_a, &full_bar[stage], kb * kBlockK, row_a, epi.hint_a);
+            tma_load_2d(sb, &map_w, &full_bar[stage], kb * kBlockK, row_w, epi.hint_w);
           } else {
             // both CTAs' bytes are credited to the leader's barrier
             if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
-            tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * kBlockK, row_a);
-            tma_load_2d_pair(sb, &map_w, &full_bar[stage], kb * kBlockK, row_w, kL2EvictLast);  // W: keep in L2
+            tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * kBlockK, row_a, epi.hint_a);
+            tma_load_2d_pair(sb, &map_w, &full_bar[stage], kb * kBlockK, row_w, epi.hint_w);  // W: keep in L2
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -267,7 +271,7 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&map_c, tile_buf, col0, row0);
+              tma_store_3d(&map_c, tile_buf, col0 % epi.slab_cols, row0, col0 / epi.slab_cols, epi.hint_c);
               tma_store_commit();
             }
             sbuf ^= 1;
@@ -296,7 +300,7 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&map_c, tile_buf, col0, row0);
+              tma_store_3d(&map_c, tile_buf, col0 % epi.slab_cols, row0, col0 / epi.slab_cols, epi.hint_c);
               tma_store_commit();
             }
             sbuf ^= 1;
@@ -363,6 +367,25 @@ bool make_tensor_map(CUtensorMap* map, const void* base, long long rows, long lo
   return r == CUDA_SUCCESS;
 }
 
+// Output map: [slabs][rows][slab_cols] (a plain matrix is one slab), boxes of 32 rows x 128 bytes.
+bool make_output_map(CUtensorMap* map, const void* base, long long rows, long long slab_cols, long long ld,
+                     long long slabs, long long slab_stride, bool f32) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return false;
+  const int esz = f32 ? 4 : 2;
+  const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(slab_cols), static_cast<cuuint64_t>(rows),
+                              static_cast<cuuint64_t>(slabs)};
+  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * esz,
+                                 static_cast<cuuint64_t>(slabs > 1 ? slab_stride : rows * ld) * esz};
+  const cuuint32_t box[3] = {static_cast<cuuint32_t>(128 / esz), 32u, 1u};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                        const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -379,7 +402,9 @@ int launch_variant(const GemmProblem& p, cudaStream_t stream, const char** err) 
   CUtensorMap map_a, map_w, map_c;
   if (!make_tensor_map(&map_a, p.a, p.m, p.k, p.lda, kBlockM) ||
       !make_tensor_map(&map_w, p.w, p.n, p.k, p.ldw, L::kBRows) ||
-      !make_tensor_map(&map_c, p.out, p.m, p.n, p.ldo, 32, p.mode == EPI_BIAS_F32)) {
+      !make_output_map(&map_c, p.out, p.m, p.slab_cols > 0 ? p.slab_cols : p.n, p.ldo,
+                       p.slab_cols > 0 ? (p.n + p.slab_cols - 1) / p.slab_cols : 1, p.slab_stride,
+                       p.mode == EPI_BIAS_F32)) {
     if (err) *err = "cuTensorMapEncodeTiled failed (pointer/pitch alignment?)";
     return TDC_ECUDA;
   }
@@ -396,12 +421,25 @@ int launch_variant(const GemmProblem& p, cudaStream_t stream, const char** err) 
                           ((p.n + BLOCK_N - 1) / BLOCK_N);
   long long clusters = num_sms() / CG;
   if (tiles < clusters) clusters = tiles;
-  EpilogueArgs e{p.bias, p.mode};
+  // L2 policy: W is re-read by every M tile -> evict_last; A and C stream.  (dev knob TDC_GEMM_HINTS=awc, one
+  // letter each for the A loads, W loads and C stores: n|f|l = normal / evict_first / evict_last)
+  static const char* hints_env = getenv("TDC_GEMM_HINTS");
+  auto pick = [](char ch, unsigned long long dflt) -> unsigned long long {
+    return ch == 'n' ? kL2EvictNormal : ch == 'f' ? kL2EvictFirst : ch == 'l' ? kL2EvictLast : dflt;
+  };
+  const bool he = hints_env != nullptr && strlen(hints_env) == 3;
+  EpilogueArgs e{p.bias, p.mode, p.slab_cols > 0 ? p.slab_cols : p.n,
+                 pick(he ? hints_env[0] : 0, kL2EvictNormal), pick(he ? hints_env[1] : 0, kL2EvictLast),
+                 pick(he ? hints_env[2] : 0, kL2EvictNormal)};
   // N-tile group whose W slice fits a quarter of the 126 MB L2 (the L2 is two ~63 MB halves and
   // read-shared lines end up in both), balanced over the groups.
   const int num_n_tiles = (p.n + BLOCK_N - 1) / BLOCK_N;
   const long long w_tile_bytes = static_cast<long long>(BLOCK_N) * p.k * 2;
-  int n_group = static_cast<int>((36ll << 20) / (w_tile_bytes > 0 ? w_tile_bytes : 1));
+  static const long long group_budget = [] {  // dev knob: TDC_GEMM_NGROUP_MB overrides the 36 MB W-slice budget
+    const char* e = getenv("TDC_GEMM_NGROUP_MB");
+    return (e != nullptr && atoi(e) > 0) ? (static_cast<long long>(atoi(e)) << 20) : (36ll << 20);
+  }();
+  int n_group = static_cast<int>(group_budget / (w_tile_bytes > 0 ? w_tile_bytes : 1));
   if (n_group < 1) n_group = 1;
   if (n_group > num_n_tiles) n_group = num_n_tiles;
   const int groups = (num_n_tiles + n_group - 1) / n_group;
@@ -442,6 +480,11 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, const char** err) {
   }
   if (p.mode != EPI_BIAS_F32 && (p.ldo % 8) != 0) {
     if (err) *err = "gemm: bf16 output pitch must be a multiple of 8 elements";
+    return TDC_EINVAL;
+  }
+  if (p.slab_cols < 0 || (p.slab_cols > 0 && ((p.slab_cols % 128) != 0 || (p.n % p.slab_cols) != 0 ||
+                                              (p.slab_stride % 8) != 0))) {
+    if (err) *err = "gemm: slab_cols must be a multiple of 128 dividing N, slab_stride a multiple of 8";
     return TDC_EINVAL;
   }
   if (p.mode < 0 || p.mode > EPI_BIAS_F32) {

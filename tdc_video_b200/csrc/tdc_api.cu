@@ -299,10 +299,11 @@ struct ForwardCall {
   } while (0)
 
 int gemm(tdc_handle* h, int cls, cudaStream_t s, const void* a, long long lda, const void* w, long long ldw,
-         const float* bias, void* out, long long ldo, long long m, int n, int k, int mode, const char** err) {
+         const float* bias, void* out, long long ldo, long long m, int n, int k, int mode, const char** err,
+         int slab_cols = 0, long long slab_stride = 0) {
   GemmProblem p;
   p.a = a; p.lda = lda; p.w = w; p.ldw = ldw; p.bias = bias; p.out = out; p.ldo = ldo;
-  p.m = static_cast<int>(m); p.n = n; p.k = k; p.mode = mode;
+  p.m = static_cast<int>(m); p.n = n; p.k = k; p.mode = mode; p.slab_cols = slab_cols; p.slab_stride = slab_stride;
   p.cta_group = h->cfg.gemm_cta_group == 0 ? 2 : h->cfg.gemm_cta_group;
   KernelScope ks(h, cls, s);
   return gemm_launch(p, s, err);
@@ -328,10 +329,16 @@ int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long
   const int kvw = 2 * H * h->n_cross;  // K/V columns per KV token over all cross layers
   const float scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
 
-  // 1. every cross layer's K and V for every KV token of every row: the dominant GEMM
+  // 1. every cross layer's K and V for every KV token of every row: the dominant GEMM.  Output layout:
+  //    one dense [rows*L, 2H] (K | V) matrix per cross layer, so that a layer's attention launch streams a
+  //    contiguous region (633 KB per row) instead of 3 KB pieces at an 18 KB stride.  2H is a multiple of
+  //    128 whenever heads is even; odd head counts fall back to the interleaved [rows*L, kvw] layout.
+  const bool kv_slabs = ((2 * H) % 128) == 0;
+  const long long kv_slab_stride = kv_slabs ? rows * L * 2ll * H : 0;
+  const long long kv_pitch = kv_slabs ? 2 * H : kvw;
   if (h->n_cross > 0)
-    TDC_TRY(gemm(h, TDC_K_KV_GEMM, s, enc, c.d_enc, h->w_ckv, c.d_enc, h->b_ckv, w.kv, kvw, rows * L, kvw, c.d_enc,
-                 EPI_BIAS_BF16, &err));
+    TDC_TRY(gemm(h, TDC_K_KV_GEMM, s, enc, c.d_enc, h->w_ckv, c.d_enc, h->b_ckv, w.kv, kv_pitch, rows * L, kvw,
+                 c.d_enc, EPI_BIAS_BF16, &err, kv_slabs ? 2 * H : 0, kv_slab_stride));
 
   // 2. embeddings + LayerNorm into the [query slab | text slab] layout
   {
@@ -383,9 +390,10 @@ int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long
       TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16, H, lw.w_cq, H, lw.b_cq, w.qc, H, MQ, H, H, EPI_BIAS_BF16, &err));
       AttentionArgs a;
       a.q = w.qc; a.out = w.ctx; a.ldq = H; a.ldo = H;
-      a.k = w.kv + static_cast<size_t>(lw.cross_index) * 2 * H;
+      a.k = kv_slabs ? w.kv + static_cast<size_t>(lw.cross_index) * kv_slab_stride
+                     : w.kv + static_cast<size_t>(lw.cross_index) * 2 * H;
       a.v = a.k + H;
-      a.ldk = a.ldv = kvw;
+      a.ldk = a.ldv = kv_pitch;
       a.rows = static_cast<int>(rows); a.heads = c.heads; a.nq = K;
       a.q_seg1 = K; a.q_seg2 = 0;
       a.kv_seg1 = L; a.kv_seg2 = 0;

@@ -24,6 +24,11 @@ struct GemmProblem {
   void* out = nullptr;  // bf16 or fp32 [M, N], row pitch ldo elements
   long long ldo = 0;
   const float* bias = nullptr;  // [N] or null
+  // Optional slab layout of the output: column n is stored in slab n / slab_cols at column n % slab_cols,
+  // slabs `slab_stride` elements apart (each slab a dense [M, slab_cols] matrix of pitch ldo).  Used to give
+  // every cross-attention layer its own contiguous K/V matrix.  slab_cols == 0: plain [M, N] output.
+  int slab_cols = 0;
+  long long slab_stride = 0;
   int mode = EPI_BIAS_BF16;
   int cta_group = 0;  // 0 = library default, 1 = single-CTA tiles, 2 = CTA-pair (cta_group::2) tiles
 };

@@ -173,3 +173,32 @@ def test_adapt_segment_matches_oracle(n_frames, dtype):
             assert float(srt[24] - srt[23]) > 2e-3
         assert torch.equal(seg.cpu(), seg_o)
     assert sum(segment_sizes(seg, len(sel))) == len(sel)
+
+
+def test_compress_is_cuda_graph_capturable():
+    """The C ABI promises stream-ordered, allocation-free, sync-free calls: capture one tdc_compress in a CUDA
+    graph, replay it on new input data in the same buffers, and compare with the eager call."""
+    from oracle.synth import QFormerGeometry, make_state_dict
+    from tdc_video_b200 import QFormerEngine
+    geom = QFormerGeometry(hidden=128, heads=2, intermediate=256, layers=2, cross_freq=2, d_enc=64, d_out=96, vocab=0)
+    eng = QFormerEngine(hidden=128, heads=2, intermediate=256, layers=2, cross_freq=2, d_enc=64, d_out=96)
+    eng.load_weights(make_state_dict(geom, 4, with_text=False))
+    q = torch.randn(9, 16, 128, device="cuda")
+    enc = torch.randn(9, 40, 64, device="cuda").bfloat16()
+    eager = eng.compress(q, enc)          # also sizes the workspace outside the capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            out = eng.compress(q, enc)
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)
+    enc.copy_(torch.randn(9, 40, 64, device="cuda").bfloat16())   # new data, same addresses
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eng.compress(q, enc))
+    assert not torch.equal(out, eager)
