@@ -5,5 +5,6 @@ short-query attention, fused row ops) in libtdc_b200.so; torch only for memory, 
 torch.distributed."""
 from ._lib import TdcError, load_library  # noqa: F401
 from .engine import QFormerEngine, avg_pool_tokens, linear  # noqa: F401
+from .projector import GeluMLPProjector, gelu_mlp  # noqa: F401
 
-__all__ = ["QFormerEngine", "TdcError", "load_library", "linear", "avg_pool_tokens"]
+__all__ = ["QFormerEngine", "TdcError", "load_library", "linear", "avg_pool_tokens", "GeluMLPProjector", "gelu_mlp"]

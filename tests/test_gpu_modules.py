@@ -202,3 +202,21 @@ def test_compress_is_cuda_graph_capturable():
     torch.cuda.synchronize()
     assert torch.equal(out, eng.compress(q, enc))
     assert not torch.equal(out, eager)
+
+
+def test_gelu_mlp_projector_module_matches_reference_sequential():
+    """`mm_projector` drop-in: same state_dict keys as nn.Sequential(Linear, GELU, Linear) (cambrian_arch.py:65-69),
+    output of tdc_gelu_mlp vs the fp32 torch modules."""
+    from tdc_video_b200 import GeluMLPProjector
+    torch.manual_seed(3)
+    ref = torch.nn.Sequential(torch.nn.Linear(1024, 3584), torch.nn.GELU(), torch.nn.Linear(3584, 3584)).eval()
+    mod = GeluMLPProjector(1024, 3584)
+    assert set(mod.state_dict()) == set(ref.state_dict())
+    mod.load_state_dict(ref.state_dict(), strict=True)
+    mod = mod.cuda().eval()
+    x = torch.randn(7, 144, 1024)
+    with torch.no_grad():
+        y_ref = ref(x)
+        y = mod(x.cuda().bfloat16())
+    assert y.shape == y_ref.shape and y.dtype == torch.bfloat16
+    _metrics_ok(y, y_ref, "mm_projector module")
