@@ -147,8 +147,9 @@ def build_problem(w, seed):
     """Synthetic video of the workload: per-row KV tokens, one query set per segment (Avg_pool-style:
     all rows of a segment share the queries derived from its static frame)."""
     from oracle.synth import QFormerGeometry, make_state_dict
-    geom = QFormerGeometry(d_enc=w["d_enc"], d_out=w["d_out"], vocab=0)
-    sd = make_state_dict(geom, seed, with_text=False)
+    T = w.get("num_text", 0)
+    geom = QFormerGeometry(d_enc=w["d_enc"], d_out=w["d_out"], vocab=30522 if T else 0)
+    sd = make_state_dict(geom, seed, with_text=T > 0)
     rows = w["segments"] * (w["frames_per_segment"] - 1)
     return geom, sd, rows
 
@@ -160,12 +161,14 @@ def cpu_baseline(geom, sd, w, sample_rows, seed):
     from oracle.synth import make_inputs
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    inp = make_inputs(geom, seed, sample_rows, w["kv_tokens"], w["num_query"], 0, audio_tokens=w["audio_tokens"])
+    T = w.get("num_text", 0)
+    inp = make_inputs(geom, seed, sample_rows, w["kv_tokens"], w["num_query"], T, audio_tokens=w["audio_tokens"])
+    ids = None if T == 0 else np.repeat(inp["input_ids"][:1], sample_rows, axis=0)   # one prompt for the whole video
     sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
     with torch.no_grad():
-        oracle.compress(sd_t, geom, inp["query_embeds"][:2], inp["enc"][:2])  # warm-up
+        oracle.compress(sd_t, geom, inp["query_embeds"][:2], inp["enc"][:2], None if ids is None else ids[:2])  # warm-up
         t0 = time.perf_counter()
-        oracle.compress(sd_t, geom, inp["query_embeds"], inp["enc"])
+        oracle.compress(sd_t, geom, inp["query_embeds"], inp["enc"], ids)
         dt = time.perf_counter() - t0
     rows_per_s = sample_rows / dt
     return rows_per_s / (w["frames_per_segment"] - 1), dt, cores
@@ -207,16 +210,19 @@ def main():
     ap.add_argument("--segments", type=int, default=0, help="override segments per GPU")
     ap.add_argument("--cpu-sample-rows", type=int, default=48)
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--e2e-rows-per-batch", type=int, default=1200)
+    ap.add_argument("--e2e-rows-per-batch", type=int, default=600,
+                    help="row batch of the host-streaming leg (smaller = shorter pipeline fill/drain; the leg is PCIe-bound)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cta-group", type=int, default=0)
+    ap.add_argument("--num-text", type=int, default=0, help="prompt tokens T shared by all rows (text_input mode; default 0 = north-star)")
     ap.add_argument("--gather-batches", type=int, default=2, help="row batches per step at N > 1 (comm/compute overlap)")
     ap.add_argument("--no-multicast", action="store_true", help="N > 1: use the NCCL all-gather instead of multicast stores")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.segments:
         w["segments"] = args.segments
+    w["num_text"] = args.num_text
     if args.impl == "reference":
         return run_reference_arm(args, w)
 
@@ -239,7 +245,8 @@ def main():
     geom, sd, rows = build_problem(w, 1234)
     L, K, d_enc, d_out = w["kv_tokens"], w["num_query"], w["d_enc"], w["d_out"]
     S = w["segments"]
-    eng = QFormerEngine(d_enc=d_enc, d_out=d_out, vocab=0, device=dev, gemm_cta_group=args.cta_group)
+    T = w["num_text"]
+    eng = QFormerEngine(d_enc=d_enc, d_out=d_out, vocab=30522 if T else 0, device=dev, gemm_cta_group=args.cta_group)
     eng.load_weights(sd)
 
     # ---- synthetic inputs, generated on the host in pinned memory (also the e2e source), then made resident
@@ -264,6 +271,10 @@ def main():
     query_set = (torch.arange(rows) // (w["frames_per_segment"] - 1)).to(torch.int32)
     enc = enc_host.to(dev)
     q_dev, qs_dev = q_sets.to(dev), query_set.to(dev)
+    ids_dev = ts_dev = None
+    if T > 0:   # one BERT-tokenised prompt per video, shared by every row (cambrian_arch.py:1532, 1643-1644)
+        ids_dev = torch.randint(1000, 30000, (1, T), generator=torch.Generator().manual_seed(7)).to(dev)
+        ts_dev = torch.zeros(rows, dtype=torch.int32, device=dev)
     gathered = torch.empty((world, rows, K, d_out), dtype=torch.bfloat16, device=dev) if world > 1 else None
     nb = max(1, args.gather_batches)
     bounds = [(rows * b // nb, rows * (b + 1) // nb) for b in range(nb)]
@@ -283,7 +294,7 @@ def main():
 
     def step():
         if world == 1:
-            return eng.compress(q_dev, enc, query_set=qs_dev, out_dtype=torch.bfloat16)
+            return eng.compress(q_dev, enc, ids_dev, query_set=qs_dev, text_set=ts_dev, out_dtype=torch.bfloat16)
         # the path's one exchange step: all-gather of the compressed tokens, issued per row batch on
         # NCCL's stream so that it overlaps the next batch's kernels; every rank ends with the
         # rank-ordered sequence [world, rows, K, d_out]
@@ -291,13 +302,14 @@ def main():
             # all-gather fused into the producing kernel: the L2-normalise kernel stores every row through
             # the multicast mapping, so all ranks receive it while the kernel runs
             for r0, r1 in bounds:
-                eng.compress_multicast(q_dev, enc[r0:r1], mcast.slot_ptr(r0), query_set=qs_dev[r0:r1],
-                                       out_dtype=torch.bfloat16)
+                eng.compress_multicast(q_dev, enc[r0:r1], mcast.slot_ptr(r0), ids_dev, query_set=qs_dev[r0:r1],
+                                       text_set=None if ts_dev is None else ts_dev[r0:r1], out_dtype=torch.bfloat16)
             mcast.barrier()
             return mcast.gathered
         works = []
         for r0, r1 in bounds:
-            out = eng.compress(q_dev, enc[r0:r1], query_set=qs_dev[r0:r1], out_dtype=torch.bfloat16)
+            out = eng.compress(q_dev, enc[r0:r1], ids_dev, query_set=qs_dev[r0:r1],
+                               text_set=None if ts_dev is None else ts_dev[r0:r1], out_dtype=torch.bfloat16)
             works.append(dist.all_gather([gathered[w, r0:r1] for w in range(world)], out, async_op=True))
         for wk in works:
             wk.wait()
@@ -340,12 +352,15 @@ def main():
     e2e = None
     if not args.no_e2e:
         out_host = torch.empty((rows, K, d_out), dtype=torch.bfloat16, pin_memory=pinned)
-        eng.compress_host(q_sets, enc_host, out_host, query_set=query_set, rows_per_batch=args.e2e_rows_per_batch)
+        e2e_kw = dict(query_set=query_set, rows_per_batch=args.e2e_rows_per_batch,
+                      input_ids=None if ids_dev is None else ids_dev.cpu(),
+                      text_set=None if ts_dev is None else ts_dev.cpu())
+        eng.compress_host(q_sets, enc_host, out_host, **e2e_kw)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.e2e_steps):
-            eng.compress_host(q_sets, enc_host, out_host, query_set=query_set, rows_per_batch=args.e2e_rows_per_batch)
+            eng.compress_host(q_sets, enc_host, out_host, **e2e_kw)
             if world > 1:
                 dist.all_gather_into_tensor(gathered.view(world * rows, K, d_out), out_host.to(dev, non_blocking=True))
                 # (e2e keeps the plain NCCL exchange: the result is read back to the host per batch anyway)
@@ -366,7 +381,7 @@ def main():
         return
 
     peaks = measured_peaks()
-    f_row, f_row_kv = flops_per_row(L, d_enc, K, 0, d_out)
+    f_row, f_row_kv = flops_per_row(L, d_enc, K, T, d_out)
     kv_ms, kv_n = prof["kv_gemm"]["ms"], prof["kv_gemm"]["launches"]
     kv_flops_per_launch = f_row_kv * rows * args.steps / max(kv_n, 1)
     kv_achieved = kv_flops_per_launch / (kv_ms / max(kv_n, 1) * 1e-3) / 1e12 if kv_ms > 0 else None
@@ -376,7 +391,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["label"], "segments_per_gpu": S, "rows_per_gpu": rows,
-                   "kv_tokens": L, "d_enc": d_enc, "d_out": d_out, "num_query": K, "num_text": 0,
+                   "kv_tokens": L, "d_enc": d_enc, "d_out": d_out, "num_query": K, "num_text": T,
                    "parallelism": f"dp{world} (video-second ranges per GPU)", "exchange": exchange,
                    "l2": f"inputs {enc.numel() * 2 / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
                    "accumulate": "fp32 (TMEM), LN/softmax/residual fp32"},

@@ -176,7 +176,8 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     tmem_relinquish<CG>();
   }
   tc_fence_before_sync();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  __syncthreads();                   // CTA-level: barrier inits + the TMEM address written by tcgen05.alloc
+  if (CG == 2) cluster_sync_all();   // pair-level: the peer's barriers are initialised before any remote arrive
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_base_smem;
 

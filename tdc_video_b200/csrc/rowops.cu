@@ -184,14 +184,28 @@ template <bool kMulticast>
 __global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restrict__ x, long long ldx,
                                                            void* __restrict__ out, int out_dtype, long long rows,
                                                            int width) {
-  // one 256-thread block per row (width is the LLM hidden size, 3-4 K); 8 elements per thread step
+  // one 256-thread block per row (width is the LLM hidden size, 3-4 K); each thread keeps its 8-element
+  // pieces in registers (up to kCache pieces = width <= 8192) so the row is read from HBM once
+  constexpr int kCache = 4;
   __shared__ float red[8];
   const long long row = blockIdx.x;
   const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  const int pieces = width / 8;
+  float4 ca[kCache], cb[kCache];
   float s = 0.f;
-  for (int j = threadIdx.x; j < width / 4; j += 256) {
-    const float4 v = xr[j];
-    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+  for (int i = 0; i < kCache; ++i) {
+    const int j = threadIdx.x + i * 256;
+    if (j < pieces) {
+      ca[i] = xr[2 * j];
+      cb[i] = xr[2 * j + 1];
+      s += ca[i].x * ca[i].x + ca[i].y * ca[i].y + ca[i].z * ca[i].z + ca[i].w * ca[i].w;
+      s += cb[i].x * cb[i].x + cb[i].y * cb[i].y + cb[i].z * cb[i].z + cb[i].w * cb[i].w;
+    }
+  }
+  for (int j = threadIdx.x + kCache * 256; j < pieces; j += 256) {  // very wide rows: not cached
+    const float4 a = xr[2 * j], b = xr[2 * j + 1];
+    s += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
   }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -201,8 +215,7 @@ __global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restri
   for (int i = 0; i < 8; ++i) tot += red[i];
   const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);  // F.normalize: x / max(||x||, eps)
   uint8_t* orow = static_cast<uint8_t*>(out) + row * width * (out_dtype == TDC_F32 ? 4 : 2);
-  for (int j = threadIdx.x; j < width / 8; j += 256) {
-    float4 a = xr[2 * j], b = xr[2 * j + 1];
+  auto emit = [&](int j, float4 a, float4 b) {
     a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
     b.x *= inv; b.y *= inv; b.z *= inv; b.w *= inv;
     if (out_dtype == TDC_F32) {
@@ -221,7 +234,13 @@ __global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restri
       }
       store16<kMulticast>(orow + j * 16, pk);
     }
+  };
+#pragma unroll
+  for (int i = 0; i < kCache; ++i) {
+    const int j = threadIdx.x + i * 256;
+    if (j < pieces) emit(j, ca[i], cb[i]);
   }
+  for (int j = threadIdx.x + kCache * 256; j < pieces; j += 256) emit(j, xr[2 * j], xr[2 * j + 1]);
 }
 
 __global__ void __launch_bounds__(256) convert_kernel(const void* __restrict__ src, int src_dtype,

@@ -220,3 +220,24 @@ def test_gelu_mlp_projector_module_matches_reference_sequential():
         y = mod(x.cuda().bfloat16())
     assert y.shape == y_ref.shape and y.dtype == torch.bfloat16
     _metrics_ok(y, y_ref, "mm_projector module")
+
+
+def test_speech_qformer_geometry():
+    """the speech Q-Former of audio_models/audio_encoder.py:11-24,98-105 is the same module at another
+    geometry (2 layers, cross-attention in every layer, ONE query token, BEATs/Whisper-width KV)."""
+    from tdc_video_b200.qformer import QFormerConfig, TDCQFormer
+    cfg = QFormerConfig(vocab_size=32, hidden_size=768, num_hidden_layers=2, num_attention_heads=12,
+                        intermediate_size=3072, max_position_embeddings=16, encoder_width=2048,
+                        cross_attention_freq=1, query_length=1)
+    model = TDCQFormer(cfg, with_lm_head=False)
+    _randomize(model, 9)
+    model = model.cuda().eval()
+    sd = {k[len("bert."):]: v.detach().cpu() for k, v in model.state_dict().items() if k.startswith("bert.")}
+    assert "encoder.layer.1.crossattention.self.key.weight" in sd        # cross_attention_freq = 1
+    B, L = 40, 17                                                         # 0.33 s windows of ~17 frames
+    q = torch.randn(B, 1, 768, device="cuda")
+    enc = torch.randn(B, L, 2048, device="cuda")
+    out = model.bert(query_embeds=q, encoder_hidden_states=enc, return_dict=True).last_hidden_state
+    ref = oracle.qformer_forward(sd, _geom_of(cfg, 0), q.cpu(), enc.cpu())
+    assert out.shape == (B, 1, 768)
+    _metrics_ok(out, ref, "speech qformer geometry")
