@@ -53,6 +53,43 @@ def adapt_segment(frame_features, max_num_segments: int = 24, window_size: int =
     return torch.tensor(indices), seg, cos
 
 
+def audio_frames_from_beats(window_embeds, sample_indices, n_frames: int, dist: int = 10):
+    """Per-frame audio tokens from BEATs window features — cambrian_arch.py:1547-1598, with the BEATs
+    forward itself (out of scope) replaced by its outputs: `window_embeds[w]` = `audio_embed` [1, t_w, 768]
+    of the w-th 10-second window (50 tokens per second).  `sample_indices[s]` = 1 when second s is a sampled
+    frame.  Every sampled frame receives the audio from its own second up to the next sampled second, pooled
+    to 50 tokens (adaptive_avg_pool2d over the token axis); the result is zero-padded to n_frames x 50."""
+    t = qo._t
+    audio_embeds, seg = [], []
+    si = [int(v) for v in torch.as_tensor(sample_indices).tolist()]
+    for w, k in enumerate(range(0, len(window_embeds) * dist, dist)):
+        audio_embed = t(window_embeds[w])
+        window = si[k:k + dist]
+        sample_len = len(window)
+        for idx, indice in enumerate(window):
+            token = audio_embed[:, idx * 50:(idx + 1) * 50, :]
+            if token.shape[1] == 0:
+                continue
+            if token.shape[1] != 50:
+                token = F.adaptive_avg_pool2d(token, (50, 768))
+            if indice == 1:
+                if seg:
+                    audio_embeds.append(F.adaptive_avg_pool2d(torch.cat(seg, dim=1), (50, 768)))
+                    seg = []
+                seg.append(token)
+                if idx + 1 < sample_len and si[k + idx + 1] == 1:
+                    audio_embeds.append(token)
+                    seg = []
+            elif indice == 0:
+                seg.append(token)
+    if seg:
+        audio_embeds.append(F.adaptive_avg_pool2d(torch.cat(seg, dim=1), (50, 768)))
+    out = torch.cat(audio_embeds).flatten(0, 1).unsqueeze(0)
+    pad = n_frames * 50 - out.size(1)
+    out = F.pad(out, (0, 0, 0, pad, 0, 0), "constant", 0)
+    return out.reshape(-1, 50, 768)
+
+
 def segment_sizes_from_boundaries(segment_frame_indices, n_frames: int):
     """cambrian_arch.py:1541-1544: boundaries after frames `segment_frame_indices` ->
     frames per segment (empty segments are possible and skipped by the loop, :1604-1605)."""

@@ -63,9 +63,24 @@ class _Tokens:
         return self
 
 
+class _StubBeats:
+    """Stands in for BEATs.extract_features (upstream model, out of scope): returns the pre-computed
+    `[1, 50 * seconds, 768]` features of the window whose id is stored in the first wav sample."""
+
+    def __init__(self, windows):
+        self.windows = windows
+        self.calls = 0
+
+    def extract_features(self, wav, padding_mask=None, feature_only=True):
+        w = int(round(float(wav[0, 0])))
+        self.calls += 1
+        return self.windows[w], None
+
+
 def run_reference_driver(weights, geom, n_frames, *, d_llm, context_token_num=16, query_type="Avg_pool",
                          text_input=True, add_static=True, tokenizer_model_max_length=100000, prompt_ids=None,
-                         dino_table=None, siglip_table=None, seed=0):
+                         dino_table=None, siglip_table=None, seed=0, audio_windows=None, video_indices=None,
+                         audio_seconds=None):
     """weights: Q-Former state dict (keys relative to `Qformer.bert.`) + `vision_proj.*`, `query_proj.*`,
     `frame_seg`, `query_tokens`, `mm_projector.weight/bias`, `image_newline`, `embed_tokens`.
     Returns dict(visual_tokens, frames, segment_frame_indices, split_sizes)."""
@@ -101,7 +116,7 @@ def run_reference_driver(weights, geom, n_frames, *, d_llm, context_token_num=16
     inner.config = SimpleNamespace(
         model_type="qwen2", image_token_len=144, query_num_list=[144], mm_projector_type="mlp2x_gelu",
         tokenizer_model_max_length=tokenizer_model_max_length, context_token_num=context_token_num,
-        audio_input=False, add_static=add_static, text_input=text_input, query_type=query_type,
+        audio_input=audio_windows is not None, add_static=add_static, text_input=text_input, query_type=query_type,
         max_num_segments=24, lowres_token=8, tokenizer_padding_side="right", hidden_size=d_llm)
     towers = [_StubTower(c1, t(siglip_table)), _StubTower(c2, t(dino_table))]
     inner.get_vision_tower_aux_list = lambda: towers
@@ -116,6 +131,16 @@ def run_reference_driver(weights, geom, n_frames, *, d_llm, context_token_num=16
     inner.embed_tokens = emb
     ids = torch.as_tensor(prompt_ids if prompt_ids is not None else [[5, 6, 7]], dtype=torch.long).reshape(1, -1)
     inner.bert_tokenizer = lambda prompt, **kw: _Tokens(ids)
+    audios = None
+    if audio_windows is not None:
+        inner.dtype = torch.float32
+        inner.audio_proj = linear("audio_proj", 768, d_llm)
+        inner.audio_encoder = SimpleNamespace(beats_path="stub", beats=_StubBeats([t(a) for a in audio_windows]))
+        secs = int(audio_seconds)
+        wav = torch.zeros(1, secs * 16000)
+        for w in range(len(audio_windows)):          # window id in the first sample of every 10-s window
+            wav[0, w * 10 * 16000] = float(w)
+        audios = [{"audio_wav": wav, "audio_wav_mask": torch.zeros(1, secs * 16000, dtype=torch.bool)}]
 
     class Fake(arch.CambrianMetaForCausalLM, nn.Module):
         def __init__(self):
@@ -140,7 +165,8 @@ def run_reference_driver(weights, geom, n_frames, *, d_llm, context_token_num=16
     with torch.no_grad():
         out = fake.prepare_inputs_labels_for_multimodal(
             input_ids, None, None, None, None, images, image_aux_attention_masks_list=None,
-            image_sizes=[(384, 384)], video_indices=[None], prompts=["what happens?"], audios=None)
+            image_sizes=[(384, 384)], video_indices=[None] if video_indices is None else [video_indices],
+            prompts=["what happens?"], audios=audios)
         new_input_embeds = out[4]
         visual = new_input_embeds[0, 1:-2]   # between embed(1) and embed(2), embed(3)
 

@@ -85,3 +85,42 @@ def test_adapt_segment_oracle_equals_reference(n_frames):
     sel, seg, cos = driver_oracle.adapt_segment(dino, 24)
     assert torch.equal(sel, sel_all[0]) and torch.equal(seg, seg_all[0])
     assert split == [len(sel)] and feats.shape[0] == len(sel)
+
+
+@pytest.mark.parametrize("pattern", ["every_second", "sparse"])
+def test_audio_branch_equals_real_reference_function(pattern):
+    """The audio branch (cambrian_arch.py:1547-1614): BEATs window features -> per-frame tokens -> audio_proj ->
+    appended to every frame's KV tokens.  BEATs itself is stubbed; everything after it is the reference's code."""
+    from oracle import harness
+    K, n_frames = 8, 27
+    if pattern == "every_second":
+        seconds = n_frames                       # 1 fps, all seconds sampled (main.py:30)
+        flags = [1] * n_frames
+        vi = torch.ones(n_frames, dtype=torch.int16)   # the audio branch needs explicit video_indices (:928, :1562)
+    else:                                       # 61-second clip, 27 sampled seconds with gaps of 1-4 seconds
+        rs = np.random.RandomState(3)
+        seconds = 61
+        pos = np.sort(rs.choice(seconds, size=n_frames, replace=False))
+        flags = [1 if i in set(pos.tolist()) else 0 for i in range(seconds)]
+        vi = torch.tensor(flags, dtype=torch.int16)
+    rs = np.random.RandomState(11)
+    n_win = (seconds + 9) // 10
+    windows = []
+    for w in range(n_win):
+        secs_w = min(10, seconds - 10 * w)
+        tlen = secs_w * 50 - (7 if w == n_win - 1 else 0)      # the last window ends 7 tokens short (ragged tail)
+        windows.append(rs.standard_normal((1, tlen, 768)).astype(np.float32))
+    w = _weights(5, K)
+    w["audio_proj.weight"] = (rs.standard_normal((D, 768)) * 0.05).astype(np.float32)
+    w["audio_proj.bias"] = (rs.standard_normal((D,)) * 0.05).astype(np.float32)
+    sig, dino = _tables(6, n_frames)
+    ref = harness.run_reference_driver(w, GEOM, n_frames, d_llm=D, context_token_num=K, prompt_ids=[[3, 9, 4, 1]],
+                                       siglip_table=sig, dino_table=dino, audio_windows=windows, video_indices=vi,
+                                       audio_seconds=seconds)
+    sizes = driver_oracle.segment_sizes_from_boundaries(ref["segment_frame_indices"], n_frames)
+    audio_frames = driver_oracle.audio_frames_from_beats(windows, flags, n_frames)
+    assert audio_frames.shape == (n_frames, 50, 768)
+    got = driver_oracle.compress_video(w, GEOM, ref["frames"], sizes, context_token_num=K, input_ids=ref["prompt_ids"],
+                                       audio_frames=audio_frames, max_visual_len=100000 - 16 - 3)
+    assert got.shape == ref["visual_tokens"].shape
+    assert float((got - ref["visual_tokens"]).abs().max()) <= 2e-5

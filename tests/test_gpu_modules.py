@@ -241,3 +241,29 @@ def test_speech_qformer_geometry():
     ref = oracle.qformer_forward(sd, _geom_of(cfg, 0), q.cpu(), enc.cpu())
     assert out.shape == (B, 1, 768)
     _metrics_ok(out, ref, "speech qformer geometry")
+
+
+@pytest.mark.parametrize("pattern", ["every_second", "sparse"])
+def test_audio_pooling_matches_oracle(pattern):
+    """tdc_video_b200.audio.pool_audio_per_frame (tdc_avg_pool_tokens kernel) vs the restated
+    cambrian_arch.py:1547-1598 (itself pinned to the real reference function in tests/test_driver_pinning.py)."""
+    from tdc_video_b200.audio import pool_audio_per_frame
+    n_frames = 27
+    rs = np.random.RandomState(3)
+    if pattern == "every_second":
+        seconds, flags = n_frames, [1] * n_frames
+    else:
+        seconds = 61
+        pos = set(np.sort(rs.choice(seconds, size=n_frames, replace=False)).tolist())
+        flags = [1 if i in pos else 0 for i in range(seconds)]
+    n_win = (seconds + 9) // 10
+    windows = []
+    for w in range(n_win):
+        tlen = min(10, seconds - 10 * w) * 50 - (7 if w == n_win - 1 else 0)
+        windows.append(torch.from_numpy(rs.standard_normal((1, tlen, 768)).astype(np.float32)))
+    ref = driver_oracle.audio_frames_from_beats(windows, flags, n_frames)
+    got = pool_audio_per_frame([w.cuda().bfloat16() for w in windows], flags, n_frames)
+    assert got.shape == ref.shape == (n_frames, 50, 768) and got.dtype == torch.bfloat16
+    assert torch.allclose(got.float().cpu(), ref, atol=3e-2, rtol=3e-2)
+    # zero padding of frames without audio (the ragged tail) is exact
+    assert torch.equal(got.float().cpu() == 0, ref == 0)
