@@ -59,7 +59,9 @@ def pool_audio_per_frame(window_embeds: Sequence[torch.Tensor], sample_indices, 
         pieces.append(_pool_to_50(torch.cat(pending, dim=1)))
     out = torch.cat(pieces, dim=0)                          # [m, 50, 768]
     if out.shape[0] > n_frames:
-        raise ValueError(f"{out.shape[0]} audio pieces for {n_frames} frames")
+        # a clip that starts with unsampled seconds yields one leading extra piece; the reference's
+        # F.pad(..., pad_size < 0) then silently crops the END of the sequence (cambrian_arch.py:1591-1595)
+        out = out[:n_frames]
     if out.shape[0] < n_frames:
         out = torch.cat([out, out.new_zeros((n_frames - out.shape[0], TOKENS_PER_SECOND, out.shape[-1]))], dim=0)
     return out
