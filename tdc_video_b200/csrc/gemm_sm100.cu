@@ -50,6 +50,7 @@ struct EpilogueArgs {
   int mode;
   int slab_cols;  // output columns per slab (== N for a plain matrix)
   unsigned long long hint_a, hint_w, hint_c;  // L2 eviction policies of the A / W loads and the C stores
+  int debug_skip;  // dev knob (TDC_GEMM_DEBUG): 1 = drain TMEM but skip the epilogue math + stores
 };
 
 template <int CG, int BLOCK_N, int STAGES>
@@ -80,19 +81,31 @@ __device__ __forceinline__ void load_bias8(const float* bias, int col, int n, fl
 // Write one thread's 32 accumulator columns (already in registers) into its row of the
 // 128B-swizzled staging tile: 16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) * 16).
 // bf16 modes: the 32 columns are 64 B = chunks [chunk0, chunk0+4); fp32: 128 B = chunks [0, 8).
+// bias of 32 consecutive columns into registers (issued before the TMEM load is waited for, so the global
+// load latency hides behind it)
+__device__ __forceinline__ void load_bias32(const float* bias, int col0, int n, float (&b)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float t[8];
+    load_bias8(bias, col0 + g * 8, n, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[g * 8 + j] = t[j];
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void stage_32_columns(const uint32_t (&v)[32], uint8_t* tile, uint32_t lane, int chunk0,
-                                                 const float* bias, int col0, int n) {
+                                                 const float (&bias)[32]) {
   uint8_t* row = tile + lane * 128;
   const uint32_t sw = lane & 7;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    float b[8], x[8];
-    load_bias8(bias, col0 + g * 8, n, b);
+    float x[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      x[j] = __uint_as_float(v[g * 8 + j]) + b[j];
-      if (MODE == EPI_BIAS_GELU_BF16) x[j] = gelu_erf_fast(x[j]);
+    for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]) + bias[g * 8 + j];
+    if (MODE == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) gelu_erf_fast_x2(x[j], x[j + 1]);
     }
     if (MODE == EPI_BIAS_F32) {
       *reinterpret_cast<float4*>(row + (((2 * g) ^ sw) << 4)) = make_float4(x[0], x[1], x[2], x[3]);
@@ -261,14 +274,16 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll 1
         for (int c = 0; c < kHalfCols / 32; ++c) {
           uint32_t v[32];
-          tmem_ld_32x32(t_addr + c * 32, v);
-          tmem_ld_wait();
+          float bias[32];
           const int col0 = col_base + c * 32;
-          if (live && col0 < n) {
+          tmem_ld_32x32(t_addr + c * 32, v);
+          load_bias32(epi.bias, col0, n, bias);
+          tmem_ld_wait();
+          if (live && col0 < n && !epi.debug_skip) {
             if (lane == 0) tma_store_wait_read<kStoreBufs - 1>();  // staging[sbuf] no longer being read
             __syncwarp();
             uint8_t* tile_buf = staging + sbuf * kStoreTileBytes;
-            stage_32_columns<EPI_BIAS_F32>(v, tile_buf, lane, 0, epi.bias, col0, n);
+            stage_32_columns<EPI_BIAS_F32>(v, tile_buf, lane, 0, bias);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -283,20 +298,23 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll 1
         for (int c = 0; c < kHalfCols / 64; ++c) {
           uint32_t v0[32], v1[32];
+          float bias0[32], bias1[32];
+          const int col0 = col_base + c * 64;
           tmem_ld_32x32(t_addr + c * 64, v0);
           tmem_ld_32x32(t_addr + c * 64 + 32, v1);
+          load_bias32(epi.bias, col0, n, bias0);
+          load_bias32(epi.bias, col0 + 32, n, bias1);
           tmem_ld_wait();
-          const int col0 = col_base + c * 64;
-          if (live && col0 < n) {
+          if (live && col0 < n && !epi.debug_skip) {
             if (lane == 0) tma_store_wait_read<kStoreBufs - 1>();
             __syncwarp();
             uint8_t* tile_buf = staging + sbuf * kStoreTileBytes;
             if (epi.mode == EPI_BIAS_GELU_BF16) {
-              stage_32_columns<EPI_BIAS_GELU_BF16>(v0, tile_buf, lane, 0, epi.bias, col0, n);
-              stage_32_columns<EPI_BIAS_GELU_BF16>(v1, tile_buf, lane, 4, epi.bias, col0 + 32, n);
+              stage_32_columns<EPI_BIAS_GELU_BF16>(v0, tile_buf, lane, 0, bias0);
+              stage_32_columns<EPI_BIAS_GELU_BF16>(v1, tile_buf, lane, 4, bias1);
             } else {
-              stage_32_columns<EPI_BIAS_BF16>(v0, tile_buf, lane, 0, epi.bias, col0, n);
-              stage_32_columns<EPI_BIAS_BF16>(v1, tile_buf, lane, 4, epi.bias, col0 + 32, n);
+              stage_32_columns<EPI_BIAS_BF16>(v0, tile_buf, lane, 0, bias0);
+              stage_32_columns<EPI_BIAS_BF16>(v1, tile_buf, lane, 4, bias1);
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -431,7 +449,8 @@ int launch_variant(const GemmProblem& p, cudaStream_t stream, const char** err) 
   const bool he = hints_env != nullptr && strlen(hints_env) == 3;
   EpilogueArgs e{p.bias, p.mode, p.slab_cols > 0 ? p.slab_cols : p.n,
                  pick(he ? hints_env[0] : 0, kL2EvictNormal), pick(he ? hints_env[1] : 0, kL2EvictLast),
-                 pick(he ? hints_env[2] : 0, kL2EvictNormal)};
+                 pick(he ? hints_env[2] : 0, kL2EvictNormal),
+                 (getenv("TDC_GEMM_DEBUG") != nullptr && atoi(getenv("TDC_GEMM_DEBUG")) == 1) ? 1 : 0};
   // N-tile group whose W slice fits a quarter of the 126 MB L2 (the L2 is two ~63 MB halves and
   // read-shared lines end up in both), balanced over the groups.
   const int num_n_tiles = (p.n + BLOCK_N - 1) / BLOCK_N;

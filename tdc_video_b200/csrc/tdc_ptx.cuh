@@ -53,12 +53,15 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Arrive on the barrier at the same smem offset in CTA `cta` of the cluster.
+// Arrive on the barrier at the same smem offset in CTA `cta` of the cluster.  Default (.release.cta)
+// semantics on purpose: the callers publish no generic-proxy data through this arrive (it hands a TMEM
+// accumulator back after tcgen05.wait::ld + tcgen05.fence), and a .release.cluster arrive costs a
+// MEMBAR.ALL + ERRBAR per call — 28 % of the epilogue warps' stall samples in the K=768 GEMMs.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(cta) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -302,6 +305,57 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(s * s * (-3.5f * 3.5f * 1.4426950408889634f)));
   e *= g;                                   // Phi(-|x|)
   return x * (x >= 0.f ? 1.0f - e : e);
+}
+
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 issue two fp32 lanes per instruction) ----------
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// gelu_erf_fast on two values at once: the degree-8 Horner chain and the surrounding multiplies run as
+// FFMA2 / FMUL2 (half the FMA-pipe instructions of the scalar form); abs / min / select / ex2 stay scalar.
+__device__ __forceinline__ void gelu_erf_fast_x2(float& x0, float& x1) {
+  const float s0 = fminf(fabsf(x0) * (0.70710678118654752440f / 3.5f), 1.0f);
+  const float s1 = fminf(fabsf(x1) * (0.70710678118654752440f / 3.5f), 1.0f);
+  const uint64_t s = pack_f32x2(s0, s1);
+#define TDC_C2(v) pack_f32x2(v, v)
+  uint64_t g = TDC_C2(2.612654719e+00f);
+  g = fma_f32x2(g, s, TDC_C2(-1.273282320e+01f));
+  g = fma_f32x2(g, s, TDC_C2(2.688603589e+01f));
+  g = fma_f32x2(g, s, TDC_C2(-3.264060733e+01f));
+  g = fma_f32x2(g, s, TDC_C2(2.571818791e+01f));
+  g = fma_f32x2(g, s, TDC_C2(-1.426494436e+01f));
+  g = fma_f32x2(g, s, TDC_C2(5.968592886e+00f));
+  g = fma_f32x2(g, s, TDC_C2(-1.969402482e+00f));
+  g = fma_f32x2(g, s, TDC_C2(4.999701200e-01f));
+  const uint64_t w = mul_f32x2(mul_f32x2(s, s), TDC_C2(-3.5f * 3.5f * 1.4426950408889634f));
+#undef TDC_C2
+  float w0, w1, e0, e1;
+  unpack_f32x2(w, w0, w1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(w0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(w1));
+  const uint64_t p = mul_f32x2(pack_f32x2(e0, e1), g);   // Phi(-|x|) for both
+  float p0, p1;
+  unpack_f32x2(p, p0, p1);
+  p0 = x0 >= 0.f ? 1.0f - p0 : p0;
+  p1 = x1 >= 0.f ? 1.0f - p1 : p1;
+  const uint64_t y = mul_f32x2(pack_f32x2(x0, x1), pack_f32x2(p0, p1));
+  unpack_f32x2(y, x0, x1);
 }
 
 }  // namespace tdc

@@ -265,5 +265,6 @@ def test_audio_pooling_matches_oracle(pattern):
     got = pool_audio_per_frame([w.cuda().bfloat16() for w in windows], flags, n_frames)
     assert got.shape == ref.shape == (n_frames, 50, 768) and got.dtype == torch.bfloat16
     assert torch.allclose(got.float().cpu(), ref, atol=3e-2, rtol=3e-2)
-    # zero padding of frames without audio (the ragged tail) is exact
-    assert torch.equal(got.float().cpu() == 0, ref == 0)
+    # frames without audio (zero padding at the end, cambrian_arch.py:1593-1595) are exactly zero in both
+    empty = (ref.abs().amax(dim=(1, 2)) == 0)
+    assert torch.equal(got.float().cpu().abs().amax(dim=(1, 2)) == 0, empty)
