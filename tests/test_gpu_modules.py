@@ -268,3 +268,30 @@ def test_audio_pooling_matches_oracle(pattern):
     # frames without audio (zero padding at the end, cambrian_arch.py:1593-1595) are exactly zero in both
     empty = (ref.abs().amax(dim=(1, 2)) == 0)
     assert torch.equal(got.float().cpu().abs().amax(dim=(1, 2)) == 0, empty)
+
+
+def test_two_engines_on_two_streams():
+    """Handles are independent and calls are stream-ordered: two engines with different weights run
+    concurrently on two non-default streams and reproduce their serial results bit for bit."""
+    from oracle.synth import QFormerGeometry, make_state_dict
+    from tdc_video_b200 import QFormerEngine
+    geom = QFormerGeometry(hidden=128, heads=2, intermediate=256, layers=2, cross_freq=2, d_enc=64, d_out=96, vocab=0)
+    engines, inputs, serial = [], [], []
+    for i in range(2):
+        eng = QFormerEngine(hidden=128, heads=2, intermediate=256, layers=2, cross_freq=2, d_enc=64, d_out=96)
+        eng.load_weights(make_state_dict(geom, 20 + i, with_text=False))
+        q = torch.randn(33, 16, 128, device="cuda")
+        enc = torch.randn(33, 50, 64, device="cuda").bfloat16()
+        engines.append(eng); inputs.append((q, enc)); serial.append(eng.compress(q, enc))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [None, None]
+    for rep in range(3):
+        for i in range(2):
+            with torch.cuda.stream(streams[i]):
+                outs[i] = engines[i].compress(*inputs[i])
+    for s in streams:
+        s.synchronize()
+    for i in range(2):
+        assert torch.equal(outs[i], serial[i])
+    assert not torch.equal(outs[0], outs[1])
