@@ -137,7 +137,12 @@ __device__ __forceinline__ TileCoord decode_tile(long long tile, int num_m_tiles
   return TileCoord{rem / width, n0 + rem % width};
 }
 
-template <int CG, int BLOCK_N, int STAGES>
+// MC = CTA pairs per cluster (CG == 2 only).  MC == 2: a 4-CTA cluster works on two vertically adjacent
+// 256-row tiles of the same N tile; the W tile they share is fetched once per cluster — every CTA loads a
+// quarter of it and TMA-multicasts it to the CTA holding the same W half in the other pair — which cuts the
+// L2 -> SM operand traffic per FLOP by 25 %.  The smem ring is then shared state of the cluster: a slot is
+// free when BOTH pairs' MMAs have retired it (empty barriers count MC commits, multicast to all CTAs).
+template <int CG, int BLOCK_N, int STAGES, int MC>
 __global__ void __launch_bounds__(kNumThreads, 1)
 tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_c, int m, int n, int k, int n_group, EpilogueArgs epi) {
@@ -156,16 +161,19 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  static_assert(MC == 1 || CG == 2, "multi-pair clusters need cta_group::2");
+  const uint32_t cluster_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const uint32_t cta_rank = cluster_rank & 1u;   // position inside the CTA pair
+  const uint32_t pair = cluster_rank >> 1;       // pair inside the cluster (0 when MC == 1)
   const bool is_leader = (cta_rank == 0);
 
-  const int tile_m_rows = kBlockM * CG;
-  const int num_m_tiles = (m + tile_m_rows - 1) / tile_m_rows;
+  const int tile_m_rows = kBlockM * CG;          // rows of one pair's tile
+  const int num_m_tiles = ((m + tile_m_rows - 1) / tile_m_rows + MC - 1) / MC;  // in units of MC stacked tiles
   const int num_n_tiles = (n + BLOCK_N - 1) / BLOCK_N;
   const long long num_tiles = static_cast<long long>(num_m_tiles) * num_n_tiles;
   const int num_kb = (k + kBlockK - 1) / kBlockK;
-  const long long first_tile = blockIdx.x / CG;
-  const long long tile_stride = gridDim.x / CG;
+  const long long first_tile = blockIdx.x / (CG * MC);
+  const long long tile_stride = gridDim.x / (CG * MC);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -175,7 +183,7 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC);  // one tcgen05.commit per pair of the cluster
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
@@ -201,7 +209,7 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       uint32_t phase = 0;
       for (long long tile = first_tile; tile < num_tiles; tile += tile_stride) {
         const TileCoord tc = decode_tile(tile, num_m_tiles, num_n_tiles, n_group);
-        const int row_a = tc.tm * tile_m_rows + static_cast<int>(cta_rank) * kBlockM;
+        const int row_a = (tc.tm * MC + static_cast<int>(pair)) * tile_m_rows + static_cast<int>(cta_rank) * kBlockM;
         const int row_w = tc.tn * BLOCK_N + static_cast<int>(cta_rank) * L::kBRows;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -215,7 +223,15 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             // both CTAs' bytes are credited to the leader's barrier
             if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
             tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * kBlockK, row_a, epi.hint_a);
-            tma_load_2d_pair(sb, &map_w, &full_bar[stage], kb * kBlockK, row_w, epi.hint_w);  // W: keep in L2
+            if (MC == 1) {
+              tma_load_2d_pair(sb, &map_w, &full_bar[stage], kb * kBlockK, row_w, epi.hint_w);  // W: keep in L2
+            } else {
+              // this CTA fetches 1/MC of its W half and multicasts it to the same-half CTA of every pair
+              constexpr int kPiece = L::kBRows / MC;
+              const uint16_t mask = static_cast<uint16_t>(0x5u << cta_rank);  // ranks {r, r + 2}
+              tma_load_2d_pair_multicast(sb + pair * (kPiece * kBlockK * 2), &map_w, &full_bar[stage], kb * kBlockK,
+                                         row_w + static_cast<int>(pair) * kPiece, mask, epi.hint_w);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -243,10 +259,11 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             // advance 16 bf16 = 32 B along K inside the swizzle span: +2 in the (addr >> 4) field
             umma_f16<CG>(d_tmem, desc_a + 2u * kk, desc_b + 2u * kk, kIdesc, (kb | kk) != 0 ? 1u : 0u);
           }
-          umma_commit<CG>(&empty_bar[stage]);  // slot reusable once these MMAs retire
+          // slot reusable once these MMAs retire (every CTA of the cluster is told)
+          umma_commit<CG>(&empty_bar[stage], static_cast<uint16_t>((1u << (CG * MC)) - 1u));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit<CG>(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        umma_commit<CG>(&tmem_full_bar[acc], static_cast<uint16_t>(0x3u << (2 * pair)));  // -> this pair's epilogues
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -263,7 +280,8 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint32_t acc_phase = 0;
     for (long long tile = first_tile; tile < num_tiles; tile += tile_stride) {
       const TileCoord tc = decode_tile(tile, num_m_tiles, num_n_tiles, n_group);
-      const int row0 = tc.tm * tile_m_rows + static_cast<int>(cta_rank) * kBlockM + static_cast<int>(quad) * 32;
+      const int row0 = (tc.tm * MC + static_cast<int>(pair)) * tile_m_rows + static_cast<int>(cta_rank) * kBlockM +
+                       static_cast<int>(quad) * 32;
       const int col_base = tc.tn * BLOCK_N + static_cast<int>(half) * kHalfCols;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after_sync();
@@ -331,7 +349,7 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       __syncwarp();
       if (lane == 0) {
         if (CG == 1) mbar_arrive(&tmem_empty_bar[acc]);
-        else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        else mbar_arrive_cluster(&tmem_empty_bar[acc], pair * 2);  // leader of this pair
       }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
@@ -415,19 +433,19 @@ int num_sms() {
   return sms;
 }
 
-template <int CG, int BLOCK_N, int STAGES>
+template <int CG, int BLOCK_N, int STAGES, int MC = 1>
 int launch_variant(const GemmProblem& p, cudaStream_t stream, const char** err) {
   using L = SmemLayout<CG, BLOCK_N, STAGES>;
   CUtensorMap map_a, map_w, map_c;
   if (!make_tensor_map(&map_a, p.a, p.m, p.k, p.lda, kBlockM) ||
-      !make_tensor_map(&map_w, p.w, p.n, p.k, p.ldw, L::kBRows) ||
+      !make_tensor_map(&map_w, p.w, p.n, p.k, p.ldw, L::kBRows / MC) ||
       !make_output_map(&map_c, p.out, p.m, p.slab_cols > 0 ? p.slab_cols : p.n, p.ldo,
                        p.slab_cols > 0 ? (p.n + p.slab_cols - 1) / p.slab_cols : 1, p.slab_stride,
                        p.mode == EPI_BIAS_F32)) {
     if (err) *err = "cuTensorMapEncodeTiled failed (pointer/pitch alignment?)";
     return TDC_ECUDA;
   }
-  auto kernel = tdc_gemm_kernel<CG, BLOCK_N, STAGES>;
+  auto kernel = tdc_gemm_kernel<CG, BLOCK_N, STAGES, MC>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotalBytes) != cudaSuccess) {
@@ -436,9 +454,27 @@ int launch_variant(const GemmProblem& p, cudaStream_t stream, const char** err) 
     }
     attr_set = true;
   }
-  const long long tiles = static_cast<long long>((p.m + kBlockM * CG - 1) / (kBlockM * CG)) *
-                          ((p.n + BLOCK_N - 1) / BLOCK_N);
-  long long clusters = num_sms() / CG;
+  const long long m_tiles = (p.m + kBlockM * CG - 1) / (kBlockM * CG);
+  const long long tiles = ((m_tiles + MC - 1) / MC) * ((p.n + BLOCK_N - 1) / BLOCK_N);
+  // persistent grid = as many clusters as can be co-resident (clusters of 4 do not tile the 148 SMs
+  // perfectly: GPCs have 16-20 SMs), otherwise the static tile striding would serialise the leftovers
+  static long long max_clusters = 0;  // per template instantiation
+  if (max_clusters == 0) {
+    max_clusters = num_sms() / (CG * MC);
+    if (CG * MC > 2) {
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(static_cast<unsigned>(num_sms() / (CG * MC) * CG * MC));
+      q.blockDim = dim3(kNumThreads);
+      q.dynamicSmemBytes = L::kTotalBytes;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CG * MC; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kernel, &q) == cudaSuccess && n > 0 && n < max_clusters) max_clusters = n;
+    }
+  }
+  long long clusters = max_clusters;
   if (tiles < clusters) clusters = tiles;
   // L2 policy: W is re-read by every M tile -> evict_last; A and C stream.  (dev knob TDC_GEMM_HINTS=awc, one
   // letter each for the A loads, W loads and C stores: n|f|l = normal / evict_first / evict_last)
@@ -466,13 +502,13 @@ int launch_variant(const GemmProblem& p, cudaStream_t stream, const char** err) 
   n_group = (num_n_tiles + groups - 1) / groups;
 
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(clusters * CG));
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * CG * MC));
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = L::kTotalBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.x = CG * MC;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -516,7 +552,12 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, const char** err) {
     // narrow outputs (small test geometries): single-CTA 128x128 tiles
     return launch_variant<1, 128, 4>(p, stream, err);
   }
-  if (cg == 2) return launch_variant<2, 256, 5>(p, stream, err);
+  if (cg == 2) {
+    // dev knob TDC_GEMM_MC=1|2: CTA pairs per cluster (2 = W multicast across two stacked tiles)
+    static const int mc = [] { const char* e = getenv("TDC_GEMM_MC"); return (e && atoi(e) == 2) ? 2 : 1; }();
+    if (mc == 2 && p.m > 2 * kBlockM * 2) return launch_variant<2, 256, 5, 2>(p, stream, err);
+    return launch_variant<2, 256, 5>(p, stream, err);
+  }
   return launch_variant<1, 256, 3>(p, stream, err);
 }
 

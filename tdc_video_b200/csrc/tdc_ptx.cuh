@@ -137,6 +137,20 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       : "memory");
 }
 
+// cta_group::2 load multicast to the CTAs in `cta_mask` (cluster ranks): the box lands at the same smem offset
+// in every destination CTA and its bytes are credited to the barrier at the same offset in the leader of the
+// destination CTA's pair.
+__device__ __forceinline__ void tma_load_2d_pair_multicast(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                           int32_t c0, int32_t c1, uint16_t cta_mask,
+                                                           uint64_t hint = kL2EvictNormal) {
+  const uint32_t bar_leader = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      ".L2::cache_hint [%0], [%1, {%4, %5}], [%2], %3, %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(bar_leader), "h"(cta_mask), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+
 // 2-D tiled store smem -> global (bulk async-group completion; out-of-bounds part is clipped).
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
@@ -220,12 +234,11 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 // Arrive on `bar` once every tcgen05 op this thread issued so far has retired.
 // CG==2: the arrive is multicast to the barrier at the same offset in both CTAs.
 template <int CG>
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint16_t mask = 0x3) {
   if (CG == 1)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
   else {
-    const uint16_t mask = 0x3;
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
             smem_u32(bar)),
