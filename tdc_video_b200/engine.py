@@ -7,6 +7,7 @@ CUDA device raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Mapping, Optional
 
 import torch
@@ -47,7 +48,8 @@ class QFormerEngine:
         self.geometry = dict(hidden=hidden, heads=heads, intermediate=intermediate, layers=layers,
                              cross_freq=cross_freq, d_enc=d_enc, d_out=d_out, vocab=vocab, max_pos=max_pos,
                              ln_eps=ln_eps)
-        self.max_workspace_bytes = int(max_workspace_bytes)
+        env_cap = os.environ.get("TDC_MAX_WORKSPACE_GB")   # dev knob: smaller workspace = smaller internal row batches
+        self.max_workspace_bytes = int(float(env_cap) * (1 << 30)) if env_cap else int(max_workspace_bytes)
         self._ws: Optional[torch.Tensor] = None
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
