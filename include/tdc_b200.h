@@ -165,6 +165,27 @@ int tdc_segment_boundaries(const void* feats, int32_t dtype, int32_t n_frames, i
                            float* cos_out, int64_t* boundaries_out, void* workspace, size_t workspace_bytes,
                            tdc_stream_t stream);
 
+/* ---- building blocks shared with the SVA connector (tdc/vision_sampler.py) ------------------ */
+/* replaces: nn.LayerNorm forward (optionally on x + resid).  x, resid fp32 [rows, width]; resid_period > 0 makes
+ * resid a [resid_period, width] table added cyclically (vision_sampler.py:376-386 position embeddings of the KV
+ * windows).  Writes y as fp32 and/or bf16 (either may be NULL). */
+int tdc_layernorm(const float* x, const float* resid, int32_t resid_period, const float* gamma, const float* beta,
+                  float eps, float* y_f32, void* y_bf16, int64_t rows, int32_t width, tdc_stream_t stream);
+
+/* replaces: torch.nn.functional.scaled_dot_product_attention with a boolean key mask and head size 64
+ * (vision_sampler.py:272-276) — and BertSelfAttention's softmax(QK^T/8)V (Qformer.py:205-268).
+ *   q / k / v / out: bf16; head h of a token at ptr + token_row * ld + h * 64
+ *   row r, query i lives at token row  q_base[i < q_seg1 ? 0 : 1] + r * q_seg{1,2} + i (- q_seg1), same for KV
+ *   kv_len  [rows] int32 or NULL; kv_mask [rows] uint32 or NULL (bit j = KV token j allowed; <= 32 KV tokens) */
+int tdc_attention(const void* q, const void* k, const void* v, void* out, int64_t ldq, int64_t ldk, int64_t ldv,
+                  int64_t ldo, int32_t rows, int32_t heads, int32_t q_seg1, int32_t q_seg2, int64_t q_base1,
+                  int64_t q_base2, int32_t kv_seg1, int32_t kv_seg2, int64_t kv_base1, int64_t kv_base2,
+                  const int32_t* kv_len, const uint32_t* kv_mask, tdc_stream_t stream);
+
+/* out = a + b in fp32 (out_f32 and/or out_bf16 may be NULL) — the outer residual of an SVA layer (:399). */
+int tdc_residual_add(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t count,
+                     tdc_stream_t stream);
+
 /* dtype conversion used by the host wrapper (fp32 / fp16 -> bf16 and back) */
 int tdc_convert(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t count, tdc_stream_t stream);
 

@@ -134,6 +134,70 @@ def make_driver_goldens(only=None):
         print(f"driver {name}: tokens {tuple(ref['visual_tokens'].shape)}")
 
 
+# ---- SVA goldens: reference VisionTokenSampler + mm_projector_aux + real window rearrangement ----------------
+# name -> (hidden, tower_dims, window_sides, layers, query_side, image sizes, seed, stress)
+SVA_CASES = {
+    "h128_masks": (128, (96, 64), (2, 2), 2, 4, [(640, 360), (384, 384), (300, 500)], 31, 3.0),
+    "h1024_full": (1024, (1152, 1536), (2, 2), 3, 12, [(1280, 720), (384, 384)], 32, 2.0),   # shipped geometry
+}
+
+
+def run_reference_sva(sd, hidden, tower_dims, sides, layers, Q, sizes, tower):
+    import importlib.util
+    name = "_tdc_reference_vision_sampler"
+    if name not in sys.modules:
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ref_shim.REFERENCE_ROOT, "tdc", "vision_sampler.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+    vs = sys.modules[name]
+    from oracle import harness
+    arch = harness._load_cambrian_arch()
+
+    class Bare(arch.CambrianMetaForCausalLM):
+        def get_model(self):
+            return None
+
+    sampler = vs.VisionTokenSampler(hidden, hidden, [hidden] * 2, list(sides), hidden, layers).eval()
+    sampler.load_state_dict({k[len("vision_sampler_0."):]: torch.from_numpy(v) for k, v in sd.items()
+                             if k.startswith("vision_sampler_0.")}, strict=True)
+    bs, nq = len(sizes), Q * Q
+    with torch.no_grad():
+        feats = []
+        for t, c in enumerate(tower_dims):
+            m = torch.nn.Sequential(torch.nn.Linear(c, hidden), torch.nn.GELU(), torch.nn.Linear(hidden, hidden),
+                                    torch.nn.LayerNorm(hidden)).eval()
+            m.load_state_dict({k[len(f"mm_projector_aux_{t}."):]: torch.from_numpy(v) for k, v in sd.items()
+                               if k.startswith(f"mm_projector_aux_{t}.")}, strict=True)
+            feats.append(m(tower[t]))
+        lat, masks = Bare().rearrange_vision_tower_features_inference(feats, Q, sizes)
+        ctx = feats[0].mean(1).view(bs, 1, 1, -1).expand(-1, nq, 1, -1).flatten(0, 1)
+        qry = torch.from_numpy(sd["vision_query"])[0].view(1, 1, 1, -1).expand(bs, nq, -1, -1).flatten(0, 1)
+        return sampler(qry, ctx, *lat, *masks).view(bs, nq, hidden)
+
+
+def sva_inputs(tower_dims, sides, Q, bs, seed):
+    rs = np.random.RandomState(seed + 5)
+    return [torch.from_numpy(rs.standard_normal((bs, (Q * s) ** 2, c)).astype(np.float32)) for s, c in zip(sides, tower_dims)]
+
+
+def make_sva_goldens(only=None):
+    from oracle.synth import make_sva_state_dict
+    for name, (hidden, dims, sides, layers, Q, sizes, seed, stress) in SVA_CASES.items():
+        if only and name not in only:
+            continue
+        sd = make_sva_state_dict(hidden, dims, sides, layers, seed, stress)
+        tower = sva_inputs(dims, sides, Q, len(sizes), seed)
+        out = run_reference_sva(sd, hidden, dims, sides, layers, Q, sizes, tower)
+        meta = dict(hidden=hidden, tower_dims=dims, window_sides=sides, layers=layers, query_side=Q, image_sizes=sizes,
+                    seed=seed, stress=stress, heads=16,
+                    generator="oracle/make_golden.py: reference VisionTokenSampler / mm_projector_aux / "
+                              "rearrange_vision_tower_features_inference (fp32 CPU)")
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"sva_{name}.npz"), meta=json.dumps(meta),
+                            out=out.numpy().astype(np.float32))
+        print(f"sva {name}: {tuple(out.shape)}")
+
+
 def main(only=None):
     assert ref_shim.reference_available(), "needs /root/reference"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -152,6 +216,7 @@ def main(only=None):
                             hidden=hidden.astype(np.float32), compressed=comp.astype(np.float32))
         print(f"{name}: hidden {hidden.shape} compressed {comp.shape}")
     make_driver_goldens(only)
+    make_sva_goldens(only)
 
 
 if __name__ == "__main__":

@@ -117,3 +117,47 @@ def make_inputs(geom: QFormerGeometry, seed: int, rows: int, kv_tokens: int, num
         lo = min(1000, max(geom.vocab - 2, 0))
         ids = rs.randint(lo if lo < geom.vocab - 1 else 0, max(geom.vocab - 1, 1), size=(rows, num_text)).astype(np.int64)
     return {"query_embeds": q, "enc": enc, "input_ids": ids}
+
+
+# ---- Spatial Vision Aggregator -----------------------------------------------------------------
+def make_sva_state_dict(hidden: int, tower_dims, window_sides, num_layers: int, seed: int, stress: float = 1.0
+                        ) -> Dict[str, np.ndarray]:
+    """Weights of `mm_projector_aux_{t}`, `vision_query` and `vision_sampler_0` with the reference's parameter
+    names (tdc/cambrian_arch.py:83-101,139-142; tdc/vision_sampler.py:305-341,170-217).  window_sides[t] =
+    tower grid side / query grid side (pos_embed_t has window_sides[t]^2 rows)."""
+    rs = np.random.RandomState(seed)
+    sd: Dict[str, np.ndarray] = {}
+    f32 = np.float32
+
+    def lin(name, out_f, in_f, bias=False, scale=None):
+        sd[name + ".weight"] = (rs.standard_normal((out_f, in_f)) * (scale or 1.0 / np.sqrt(in_f))).astype(f32)
+        if bias:
+            sd[name + ".bias"] = (rs.standard_normal((out_f,)) * 0.05).astype(f32)
+
+    def ln(name, n):
+        sd[name + ".weight"] = (1.0 + 0.1 * rs.standard_normal((n,))).astype(f32)
+        sd[name + ".bias"] = (0.1 * rs.standard_normal((n,))).astype(f32)
+
+    for t, c in enumerate(tower_dims):
+        lin(f"mm_projector_aux_{t}.0", hidden, c, bias=True)
+        lin(f"mm_projector_aux_{t}.2", hidden, hidden, bias=True)
+        ln(f"mm_projector_aux_{t}.3", hidden)
+    sd["vision_query"] = rs.standard_normal((1, hidden)).astype(f32)
+    for i in range(num_layers):
+        p = f"vision_sampler_0.layers.{i}."
+        lin(p + "proj_context", hidden, hidden)
+        lin(p + "proj_in", hidden, 2 * hidden)
+        lin(p + "proj_out.linear_1", hidden, hidden)
+        lin(p + "proj_out.linear_2", hidden, hidden)
+        ln(p + "norm", hidden)
+        ln(p + "cross_attn.q_proj.0", hidden)
+        lin(p + "cross_attn.q_proj.1", hidden, hidden, scale=stress / np.sqrt(hidden))
+        for t, side in enumerate(window_sides):
+            ln(p + f"cross_attn.k_proj_{t}.0", hidden)
+            lin(p + f"cross_attn.k_proj_{t}.1", hidden, hidden, scale=stress / np.sqrt(hidden))
+            ln(p + f"cross_attn.v_proj_{t}.0", hidden)
+            lin(p + f"cross_attn.v_proj_{t}.1", hidden, hidden)
+            if side > 1:
+                sd[p + f"pos_embed_{t}"] = rs.standard_normal((side * side, hidden)).astype(f32)
+        lin(p + "cross_attn.o_proj", hidden, hidden)
+    return sd

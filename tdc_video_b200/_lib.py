@@ -25,7 +25,7 @@ KERNEL_CLASS_NAMES = ["kv_gemm", "query_gemm", "attention", "rowops"]
 EXPORTED_SYMBOLS = [
     "tdc_abi_version", "tdc_create", "tdc_destroy", "tdc_last_error", "tdc_load_weights", "tdc_workspace_bytes",
     "tdc_qformer_forward", "tdc_proj_norm", "tdc_compress", "tdc_compress_multicast", "tdc_linear", "tdc_gelu_mlp", "tdc_avg_pool_tokens",
-    "tdc_convert", "tdc_segment_workspace_bytes", "tdc_segment_boundaries", "tdc_set_profiling", "tdc_get_profile", "tdc_reset_profile", "tdc_launch_count",
+    "tdc_convert", "tdc_layernorm", "tdc_attention", "tdc_residual_add", "tdc_segment_workspace_bytes", "tdc_segment_boundaries", "tdc_set_profiling", "tdc_get_profile", "tdc_reset_profile", "tdc_launch_count",
 ]
 
 
@@ -65,6 +65,12 @@ def _declare(lib: C.CDLL) -> None:
     lib.tdc_gelu_mlp.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.tdc_avg_pool_tokens.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
     lib.tdc_convert.argtypes = [vp, i32, vp, i32, i64, vp]
+    lib.tdc_layernorm.argtypes = [vp, vp, i32, vp, vp, C.c_float, vp, vp, i64, i32, vp]
+    lib.tdc_attention.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i32, i32, i32, i32, i64, i64, i32, i32, i64, i64,
+                                  vp, vp, vp]
+    lib.tdc_residual_add.argtypes = [vp, vp, vp, vp, i64, vp]
+    for _n in ("tdc_layernorm", "tdc_attention", "tdc_residual_add"):
+        getattr(lib, _n).restype = C.c_int
     lib.tdc_segment_workspace_bytes.argtypes = [i32, i64]
     lib.tdc_segment_workspace_bytes.restype = sz
     lib.tdc_segment_boundaries.argtypes = [vp, i32, i32, i64, i32, vp, vp, vp, sz, vp]

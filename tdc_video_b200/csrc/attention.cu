@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(128, 4) tdc_attention_kernel(AttentionArgs a) 
   const int r = static_cast<int>(wid / (static_cast<long long>(a.heads) * nqb));
 
   const int kv_total = a.kv_seg1 + a.kv_seg2;
+  const uint32_t mbits = a.kv_mask != nullptr ? a.kv_mask[r] : 0xffffffffu;
   int kvn = kv_total;
   if (a.kv_len != nullptr) {
     kvn = a.kv_len[r];
@@ -172,7 +173,9 @@ __global__ void __launch_bounds__(128, 4) tdc_attention_kernel(AttentionArgs a) 
     }
     // ---- scale, mask the tail, online softmax (rows g and g+8)
     const int tc = t0 + c * 2;
-    const bool v00 = tc < kvn, v01 = tc + 1 < kvn, v10 = tc + 8 < kvn, v11 = tc + 9 < kvn;
+    const bool v00 = tc < kvn && ((mbits >> (tc & 31)) & 1u), v01 = tc + 1 < kvn && ((mbits >> ((tc + 1) & 31)) & 1u);
+    const bool v10 = tc + 8 < kvn && ((mbits >> ((tc + 8) & 31)) & 1u);
+    const bool v11 = tc + 9 < kvn && ((mbits >> ((tc + 9) & 31)) & 1u);
     s0[0] = v00 ? s0[0] * a.scale_log2 : -INFINITY;
     s0[1] = v01 ? s0[1] * a.scale_log2 : -INFINITY;
     s0[2] = v00 ? s0[2] * a.scale_log2 : -INFINITY;
@@ -187,9 +190,14 @@ __global__ void __launch_bounds__(128, 4) tdc_attention_kernel(AttentionArgs a) 
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // finite: token t0 is always valid
-    const float al0 = exp2f(m0 - mn0), al1 = exp2f(m1 - mn1);
-    m0 = mn0; m1 = mn1;
+    const float mp0 = m0, mp1 = m1;  // running maxima before this group
+    m0 = fmaxf(m0, mx0);
+    m1 = fmaxf(m1, mx1);
+    // safe subtrahend: with a kv_mask a whole group (or everything so far) can be masked; exp2(-inf - (-inf))
+    // must not enter the arithmetic — such rows simply keep P = 0, O = 0, l = 0 until a valid token arrives
+    const float mn0 = (m0 == -INFINITY) ? 0.f : m0;
+    const float mn1 = (m1 == -INFINITY) ? 0.f : m1;
+    const float al0 = exp2f(mp0 - mn0), al1 = exp2f(mp1 - mn1);
     const float p00 = exp2f(s0[0] - mn0), p01 = exp2f(s0[1] - mn0), p02 = exp2f(s1[0] - mn0), p03 = exp2f(s1[1] - mn0);
     const float p10 = exp2f(s0[2] - mn1), p11 = exp2f(s0[3] - mn1), p12 = exp2f(s1[2] - mn1), p13 = exp2f(s1[3] - mn1);
     l0 = l0 * al0 + (p00 + p01 + p02 + p03);
@@ -250,6 +258,10 @@ __global__ void __launch_bounds__(128, 4) tdc_attention_kernel(AttentionArgs a) 
 int attention_launch(const AttentionArgs& a, cudaStream_t stream, const char** err) {
   if (a.rows <= 0 || a.nq <= 0 || a.heads <= 0 || a.kv_seg1 + a.kv_seg2 <= 0) {
     if (err) *err = "attention: empty problem";
+    return TDC_EINVAL;
+  }
+  if (a.kv_mask != nullptr && a.kv_seg1 + a.kv_seg2 > 32) {
+    if (err) *err = "attention: kv_mask supports at most 32 KV tokens per row";
     return TDC_EINVAL;
   }
   if ((a.ldq % 8) || (a.ldk % 8) || (a.ldv % 8) || (a.ldo % 8)) {

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
                                                         float* y_f32, __nv_bfloat16* __restrict__ y_bf16,
-                                                        long long ldy, long long rows, int width) {
+                                                        long long ldy, long long rows, int width, int resid_period) {
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   for (int j = 0; j < kMaxVec; ++j)
     if (j < nv && lane + 32 * j < width / 4) v[j] = xr[lane + 32 * j];
   if (resid != nullptr) {  // post-LN residual: LN(dense(x) + input), Qformer.py:285-289 / 371-375
-    const float4* rr = reinterpret_cast<const float4*>(resid + row * ldr);
+    const long long rrow = resid_period > 0 ? row % resid_period : row;
+    const float4* rr = reinterpret_cast<const float4*>(resid + rrow * ldr);
 #pragma unroll
     for (int j = 0; j < kMaxVec; ++j)
       if (j < nv && lane + 32 * j < width / 4) {
@@ -250,6 +251,18 @@ __global__ void __launch_bounds__(256) convert_kernel(const void* __restrict__ s
     store4_from_f32(dst, dst_dtype, i, load4_as_f32(src, src_dtype, i));
 }
 
+__global__ void __launch_bounds__(256) residual_add_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                           float* __restrict__ out_f32,
+                                                           __nv_bfloat16* __restrict__ out_bf16, long long count4) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count4; i += stride) {
+    const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
+    const float4 z = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+    if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32)[i] = z;
+    if (out_bf16 != nullptr) store4_from_f32(out_bf16, TDC_BF16, i, z);
+  }
+}
+
 __global__ void __launch_bounds__(256) take_query_tokens_kernel(const void* __restrict__ hidden, int dtype, int rows,
                                                                 int tokens_per_row, int num_query, int width,
                                                                 __nv_bfloat16* __restrict__ out) {
@@ -293,14 +306,15 @@ int check_launch(const char** err) {
 
 int layernorm_launch(const float* x, long long ldx, const float* resid, long long ldr, const float* gamma,
                      const float* beta, float eps, float* y_f32, __nv_bfloat16* y_bf16, long long ldy, long long rows,
-                     int width, cudaStream_t stream, const char** err) {
+                     int width, cudaStream_t stream, const char** err, int resid_period) {
   if (rows <= 0) return TDC_OK;
   if (width % 4 != 0 || width > kMaxVec * 128 || ldx % 4 != 0 || ldy % 4 != 0 || ldr % 4 != 0) {
     if (err) *err = "layernorm: width must be a multiple of 4 and <= 1024";
     return TDC_EINVAL;
   }
   layernorm_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(x, ldx, resid, ldr, gamma, beta, eps,
-                                                                              y_f32, y_bf16, ldy, rows, width);
+                                                                              y_f32, y_bf16, ldy, rows, width,
+                                                                              resid_period);
   return check_launch(err);
 }
 
@@ -348,6 +362,19 @@ int convert_launch(const void* src, int src_dtype, void* dst, int dst_dtype, lon
   long long blocks = (count / 4 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   convert_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(src, src_dtype, dst, dst_dtype, count / 4);
+  return check_launch(err);
+}
+
+int residual_add_launch(const float* a, const float* b, float* out_f32, __nv_bfloat16* out_bf16, long long count,
+                        cudaStream_t stream, const char** err) {
+  if (count <= 0) return TDC_OK;
+  if (count % 4 != 0) {
+    if (err) *err = "residual_add: element count must be a multiple of 4";
+    return TDC_EINVAL;
+  }
+  long long blocks = (count / 4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  residual_add_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(a, b, out_f32, out_bf16, count / 4);
   return check_launch(err);
 }
 

@@ -670,6 +670,60 @@ int tdc_avg_pool_tokens(const void* frames, int32_t dtype, int32_t n, int32_t to
   return rc;
 }
 
+int tdc_layernorm(const float* x, const float* resid, int32_t resid_period, const float* gamma, const float* beta,
+                  float eps, float* y_f32, void* y_bf16, int64_t rows, int32_t width, tdc_stream_t stream) {
+  if (rows == 0) return TDC_OK;
+  if (x == nullptr || gamma == nullptr || beta == nullptr || (y_f32 == nullptr && y_bf16 == nullptr) || rows < 0 ||
+      resid_period < 0) {
+    g_create_error = "tdc_layernorm: null pointer / bad argument";
+    return TDC_EINVAL;
+  }
+  const char* err = nullptr;
+  const int rc = layernorm_launch(x, width, resid, width, gamma, beta, eps, y_f32, static_cast<__nv_bfloat16*>(y_bf16),
+                                  width, rows, width, static_cast<cudaStream_t>(stream), &err, resid_period);
+  if (rc != TDC_OK) g_create_error = err ? err : "tdc_layernorm failed";
+  return rc;
+}
+
+int tdc_attention(const void* q, const void* k, const void* v, void* out, int64_t ldq, int64_t ldk, int64_t ldv,
+                  int64_t ldo, int32_t rows, int32_t heads, int32_t q_seg1, int32_t q_seg2, int64_t q_base1,
+                  int64_t q_base2, int32_t kv_seg1, int32_t kv_seg2, int64_t kv_base1, int64_t kv_base2,
+                  const int32_t* kv_len, const uint32_t* kv_mask, tdc_stream_t stream) {
+  if (rows == 0) return TDC_OK;
+  if (q == nullptr || k == nullptr || v == nullptr || out == nullptr || q_seg1 < 0 || q_seg2 < 0 || kv_seg1 < 0 ||
+      kv_seg2 < 0) {
+    g_create_error = "tdc_attention: null pointer / bad argument";
+    return TDC_EINVAL;
+  }
+  AttentionArgs a;
+  a.q = static_cast<const __nv_bfloat16*>(q); a.k = static_cast<const __nv_bfloat16*>(k);
+  a.v = static_cast<const __nv_bfloat16*>(v); a.out = static_cast<__nv_bfloat16*>(out);
+  a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
+  a.rows = rows; a.heads = heads; a.nq = q_seg1 + q_seg2;
+  a.q_seg1 = q_seg1; a.q_seg2 = q_seg2; a.q_base1 = q_base1; a.q_base2 = q_base2;
+  a.kv_seg1 = kv_seg1; a.kv_seg2 = kv_seg2; a.kv_base1 = kv_base1; a.kv_base2 = kv_base2;
+  a.kv_len = kv_len; a.kv_mask = kv_mask;
+  a.scale_log2 = 1.4426950408889634f / 8.0f;
+  const char* err = nullptr;
+  const int rc = attention_launch(a, static_cast<cudaStream_t>(stream), &err);
+  if (rc != TDC_OK) g_create_error = err ? err : "tdc_attention failed";
+  return rc;
+}
+
+int tdc_residual_add(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t count,
+                     tdc_stream_t stream) {
+  if (count == 0) return TDC_OK;
+  if (a == nullptr || b == nullptr || (out_f32 == nullptr && out_bf16 == nullptr) || count < 0) {
+    g_create_error = "tdc_residual_add: null pointer / bad argument";
+    return TDC_EINVAL;
+  }
+  const char* err = nullptr;
+  const int rc = residual_add_launch(a, b, out_f32, static_cast<__nv_bfloat16*>(out_bf16), count,
+                                     static_cast<cudaStream_t>(stream), &err);
+  if (rc != TDC_OK) g_create_error = err ? err : "tdc_residual_add failed";
+  return rc;
+}
+
 size_t tdc_segment_workspace_bytes(int32_t n_frames, int64_t dim) {
   if (n_frames < 2 || dim <= 0) return 0;
   return static_cast<size_t>(n_frames - 1) * frame_cosine_slices(dim) * 3 * sizeof(float);

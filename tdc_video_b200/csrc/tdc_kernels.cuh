@@ -27,16 +27,23 @@ struct AttentionArgs {
   int kv_seg1 = 0, kv_seg2 = 0;
   long long kv_base1 = 0, kv_base2 = 0;
   const int32_t* kv_len = nullptr;  // [rows] or null
+  const uint32_t* kv_mask = nullptr;  // [rows] or null: bit j = KV token j may be attended (needs <= 32 KV tokens)
   float scale_log2 = 0.f;           // log2(e) / sqrt(head size)
 };
 int attention_launch(const AttentionArgs& a, cudaStream_t stream, const char** err);
 
 // y = LayerNorm(x + resid) * gamma + beta, fp32 statistics (tdc/Qformer.py:285-289, 371-375).
 // x, resid (nullable) fp32 [rows, width]; writes y as fp32 (nullable) and bf16 (nullable).
-// y_f32 may alias resid (each warp reads its whole row before writing it).
+// y_f32 may alias resid (each warp reads its whole row before writing it).  resid_period > 0: the residual is a
+// [resid_period, width] table added cyclically (row r uses table row r % resid_period) — the SVA position
+// embeddings of the KV windows (tdc/vision_sampler.py:376-386).
 int layernorm_launch(const float* x, long long ldx, const float* resid, long long ldr, const float* gamma,
                      const float* beta, float eps, float* y_f32, __nv_bfloat16* y_bf16, long long ldy, long long rows,
-                     int width, cudaStream_t stream, const char** err);
+                     int width, cudaStream_t stream, const char** err, int resid_period = 0);
+
+// out = a + b (fp32), optionally also as bf16 — the outer residual of the SVA layer (vision_sampler.py:399).
+int residual_add_launch(const float* a, const float* b, float* out_f32, __nv_bfloat16* out_bf16, long long count,
+                        cudaStream_t stream, const char** err);
 
 // BertEmbeddings.forward (tdc/Qformer.py:78-108): query tokens = query_embeds (no position
 // embedding), text tokens = word_emb[id] + pos_emb[t]; LayerNorm over everything.

@@ -244,8 +244,9 @@ class QFormerEngine:
 
 # ---- free functions (no handle) -----------------------------------------------------------
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, gelu=False,
-           out_dtype=torch.bfloat16, cta_group=0) -> torch.Tensor:
-    """y = x . weight^T + bias on the tcgen05 GEMM (tdc_linear).  x [..., k], weight [n, k]."""
+           out_dtype=torch.bfloat16, cta_group=0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = x . weight^T + bias on the tcgen05 GEMM (tdc_linear).  x [..., k], weight [n, k].
+    `out`: optional preallocated contiguous [m, n] destination (e.g. a row slice of a larger buffer)."""
     lib = _lib.load_library()
     if not x.is_cuda:
         raise RuntimeError("tdc_video_b200.linear needs CUDA tensors: there is no CPU fallback")
@@ -254,12 +255,18 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     x2 = x.reshape(-1, k).to(torch.bfloat16).contiguous()
     w = weight.to(x.device, torch.bfloat16).contiguous()
     b = None if bias is None else bias.to(x.device, torch.float32).contiguous()
-    y = torch.empty((x2.shape[0], n), dtype=out_dtype, device=x.device)
-    with torch.cuda.device(x.device):
-        rc = lib.tdc_linear(_ptr(x2), _ptr(w), _ptr(b), _ptr(y), x2.shape[0], n, k, _DTYPES[out_dtype], int(gelu),
-                            cta_group, _stream(x.device))
-    check(rc, None, "tdc_linear")
-    return y.reshape(*x.shape[:-1], n)
+    if out is not None:
+        if out.shape != (x2.shape[0], n) or not out.is_contiguous() or out.device != x.device:
+            raise ValueError("linear(out=...): need a contiguous [m, n] tensor on the input's device")
+        y, out_dtype = out, out.dtype
+    else:
+        y = torch.empty((x2.shape[0], n), dtype=out_dtype, device=x.device)
+    if x2.shape[0] > 0:
+        with torch.cuda.device(x.device):
+            rc = lib.tdc_linear(_ptr(x2), _ptr(w), _ptr(b), _ptr(y), x2.shape[0], n, k, _DTYPES[out_dtype], int(gelu),
+                                cta_group, _stream(x.device))
+        check(rc, None, "tdc_linear")
+    return y if out is not None else y.reshape(*x.shape[:-1], n)
 
 
 def avg_pool_tokens(frames: torch.Tensor, num_query: int) -> torch.Tensor:

@@ -1,0 +1,212 @@
+"""Spatial Vision Aggregator (SVA) connector on the B200 kernels — SURVEY §8f-3.
+
+Reference: `mm_projector_aux_{t}` (tdc/cambrian_arch.py:83-93, applied :1002-1013), the window rearrangement and
+attention masks (:601-690, :487-509) and `vision_sampler_{g}` = `VisionTokenSampler` of joint
+`VisionCrossAttentionLayer`s with `MultiKVCrossAttention` (tdc/vision_sampler.py:170-291, 305-401, 519-566), as driven
+from cambrian_arch.py:1002-1053: every one of the Q x Q learnable queries of a frame cross-attends to the r x r
+window of tokens under it in each vision tower's feature grid.
+
+`SVAConnector` keeps the reference's attribute and parameter names (`mm_projector_aux_0`, `vision_query`,
+`vision_sampler_0.layers.{i}.cross_attn.k_proj_0.1.weight`, ...), so the `model.*` entries of a reference checkpoint
+load unchanged.  The forward is a sequence of libtdc_b200 calls: tcgen05 GEMMs (`tdc_linear`, GELU fused), the
+fused (residual / position-embedding +) LayerNorm (`tdc_layernorm`), the short-query attention kernel with a
+per-row key mask (`tdc_attention`; one query against r0^2 + r1^2 keys, two-segment KV = the two towers) and
+`tdc_residual_add`.  torch does data movement only (window permutation, concatenation, broadcast).  CUDA only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .engine import _ptr, _stream, avg_pool_tokens, linear
+
+LN_EPS = 1e-5
+
+
+def window_mask_bits(image_sizes: Sequence[Tuple[int, int]], grids: Sequence[int], query_side: int) -> np.ndarray:
+    """uint32 [bs * Q^2]: bit j set = KV token j of the row (tower 0's window tokens first, then tower 1's) is real
+    image content.  Integer restatement of unmask_attention_mask + the per-window regrouping
+    (cambrian_arch.py:487-509, 619-669); all-padding windows are fully enabled, as in the reference (:667-669)."""
+    out = []
+    for (w, h) in image_sizes:
+        per_tower = []
+        for grid in grids:
+            m = np.ones((grid, grid), dtype=bool)
+            if (w / h) > 1.0:
+                pad = (grid - int(h * (grid / w))) // 2
+                if pad > 0:
+                    m[:pad, :] = False
+                    m[-pad:, :] = False
+            else:
+                pad = (grid - int(w * (grid / h))) // 2
+                if pad > 0:
+                    m[:, :pad] = False
+                    m[:, -pad:] = False
+            r = grid // query_side
+            win = m.reshape(query_side, r, query_side, r).transpose(0, 2, 1, 3).reshape(query_side * query_side, r * r)
+            win[win.sum(-1) == 0] = True
+            per_tower.append(win)
+        bits = np.zeros(query_side * query_side, dtype=np.uint64)
+        shift = 0
+        for win in per_tower:
+            for j in range(win.shape[1]):
+                bits |= win[:, j].astype(np.uint64) << np.uint64(shift + j)
+            shift += win.shape[1]
+        out.append(bits.astype(np.uint32))
+    return np.concatenate(out) if out else np.zeros(0, np.uint32)
+
+
+def _layernorm(x: torch.Tensor, ln: nn.LayerNorm, *, resid: Optional[torch.Tensor] = None, resid_period: int = 0,
+               want_f32: bool = False):
+    """LayerNorm(x [+ resid]) through tdc_layernorm: x fp32 [rows, width] -> bf16 (and fp32 if asked)."""
+    lib = _lib.load_library()
+    rows, width = x.shape
+    y16 = torch.empty((rows, width), dtype=torch.bfloat16, device=x.device)
+    y32 = torch.empty((rows, width), dtype=torch.float32, device=x.device) if want_f32 else None
+    with torch.cuda.device(x.device):
+        rc = lib.tdc_layernorm(_ptr(x), _ptr(resid), resid_period, _ptr(ln.weight), _ptr(ln.bias), float(ln.eps),
+                               _ptr(y32), _ptr(y16), rows, width, _stream(x.device))
+    _lib.check(rc, None, "tdc_layernorm")
+    return (y16, y32) if want_f32 else y16
+
+
+class _Params(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container: the computation runs in libtdc_b200.so")
+
+
+def _ln_linear(d_in: int, d_out: int) -> nn.Sequential:
+    return nn.Sequential(nn.LayerNorm(d_in), nn.Linear(d_in, d_out, bias=False))
+
+
+def _cross_attention_layer(hidden: int, window_sides: Sequence[int]) -> nn.Module:
+    layer = _Params()
+    layer.proj_context = nn.Linear(hidden, hidden, bias=False)
+    layer.proj_in = nn.Linear(2 * hidden, hidden, bias=False)
+    layer.proj_out = _Params()
+    layer.proj_out.linear_1 = nn.Linear(hidden, hidden, bias=False)
+    layer.proj_out.linear_2 = nn.Linear(hidden, hidden, bias=False)
+    layer.norm = nn.LayerNorm(hidden)
+    layer.cross_attn = _Params()
+    layer.cross_attn.q_proj = _ln_linear(hidden, hidden)
+    for t, side in enumerate(window_sides):
+        setattr(layer.cross_attn, f"k_proj_{t}", _ln_linear(hidden, hidden))
+        setattr(layer.cross_attn, f"v_proj_{t}", _ln_linear(hidden, hidden))
+        if side > 1:
+            setattr(layer, f"pos_embed_{t}", nn.Parameter(torch.randn(side * side, hidden)))
+    layer.cross_attn.o_proj = nn.Linear(hidden, hidden, bias=False)
+    return layer
+
+
+class SVAConnector(nn.Module):
+    """`mm_projector_aux_{t}` + `vision_query` + `vision_sampler_0` of the reference model (one query group whose
+    grid equals the final token grid: query_num_list == [image_token_len], the shipped configuration)."""
+
+    def __init__(self, tower_dims: Sequence[int], window_sides: Sequence[int], hidden: int = 1024, query_side: int = 12,
+                 num_layers: int = 3):
+        super().__init__()
+        if len(tower_dims) != 2 or len(window_sides) != 2:
+            raise NotImplementedError("two vision towers (SigLIP + DINOv2) as in the reference; the attention kernel "
+                                      "addresses the two towers as its two KV segments")
+        if hidden % 64 != 0:
+            raise ValueError("libtdc_b200 attention has head size 64: hidden must be a multiple of 64 "
+                             "(reference: 1024 = 16 heads x 64)")
+        if sum(s * s for s in window_sides) > 32:
+            raise ValueError("at most 32 KV tokens per query (per-row key mask is 32 bits)")
+        self.hidden, self.query_side, self.num_layers = hidden, query_side, num_layers
+        self.window_sides = tuple(int(s) for s in window_sides)
+        for t, c in enumerate(tower_dims):
+            setattr(self, f"mm_projector_aux_{t}", nn.Sequential(nn.Linear(c, hidden), nn.GELU(),
+                                                                 nn.Linear(hidden, hidden), nn.LayerNorm(hidden)))
+        self.vision_query = nn.Parameter(torch.randn(1, hidden))
+        self.vision_sampler_0 = _Params()
+        self.vision_sampler_0.layers = nn.ModuleList(
+            [_cross_attention_layer(hidden, self.window_sides) for _ in range(num_layers)])
+        self._bf16 = {}
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._bf16.clear())
+        self.eval()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._bf16 = {}
+        return out
+
+    def _w(self, lin: nn.Linear) -> torch.Tensor:
+        """bf16 copy of a weight, made once (cleared by load_state_dict / .to())."""
+        key = id(lin)
+        if key not in self._bf16:
+            self._bf16[key] = lin.weight.detach().to(torch.bfloat16).contiguous()
+        return self._bf16[key]
+
+    @torch.no_grad()
+    def forward(self, tower_feats: Sequence[torch.Tensor], image_sizes: Sequence[Tuple[int, int]]) -> torch.Tensor:
+        """tower_feats[t]: [bs, grid_t^2, C_t] (CUDA); image_sizes[b] = (width, height) of frame b before padding.
+        Returns the query features [bs, Q^2, hidden] (bf16) that feed `mm_projector` (cambrian_arch.py:1146-1150)."""
+        if self.training:
+            raise RuntimeError("SVAConnector is inference-only (eval mode)")
+        if not tower_feats[0].is_cuda:
+            raise RuntimeError("SVAConnector needs CUDA tensors: there is no CPU fallback")
+        lib = _lib.load_library()
+        dev = tower_feats[0].device
+        bs, Q, H = tower_feats[0].shape[0], self.query_side, self.hidden
+        R = bs * Q * Q
+        grids = [int(round(f.shape[1] ** 0.5)) for f in tower_feats]
+        for g, s in zip(grids, self.window_sides):
+            if g != Q * s:
+                raise ValueError(f"tower grid {g} != query_side {Q} x window side {s}")
+        # --- mm_projector_aux_t: Linear . GELU . Linear . LayerNorm  (cambrian_arch.py:1002-1013)
+        latents, feat0 = [], None
+        for t, x in enumerate(tower_feats):
+            seq = getattr(self, f"mm_projector_aux_{t}")
+            h = linear(x.to(torch.bfloat16), self._w(seq[0]), seq[0].bias, gelu=True)
+            y = linear(h, self._w(seq[2]), seq[2].bias, out_dtype=torch.float32).reshape(-1, H)
+            _, f32 = _layernorm(y, seq[3], want_f32=True)
+            f32 = f32.view(bs, grids[t] * grids[t], H)
+            if t == 0:
+                feat0 = f32
+            r = self.window_sides[t]
+            # tokens under every query, window-major (cambrian_arch.py:624-645): pure data movement
+            latents.append(f32.view(bs, Q, r, Q, r, H).permute(0, 1, 3, 2, 4, 5).reshape(R * r * r, H).contiguous())
+        context = avg_pool_tokens(feat0, 1).reshape(bs, H)                       # global context = token mean (:1009)
+        q32 = self.vision_query.detach()[0].float().view(1, H).expand(R, H).contiguous()
+        q16 = q32.to(torch.bfloat16)
+        mask = torch.from_numpy(window_mask_bits(image_sizes, grids, Q).view(np.int32)).to(dev)
+        n0, n1 = self.window_sides[0] ** 2, self.window_sides[1] ** 2
+        rows0 = R * n0                                                           # K/V rows of tower 0 precede tower 1's
+        kbuf = torch.empty((R * (n0 + n1), H), dtype=torch.bfloat16, device=dev)
+        vbuf = torch.empty_like(kbuf)
+        att = torch.empty((R, H), dtype=torch.bfloat16, device=dev)
+        for layer in self.vision_sampler_0.layers:
+            ca = layer.cross_attn
+            # proj_context + cat + proj_in (vision_sampler.py:346-360); the context is one vector per frame
+            ctx = linear(context, self._w(layer.proj_context))                   # [bs, H] bf16
+            cat = torch.cat([q16, ctx.repeat_interleave(Q * Q, dim=0)], dim=-1)  # [R, 2H] bf16
+            q1 = linear(cat, self._w(layer.proj_in), out_dtype=torch.float32)    # fp32 residual of the inner block
+            qs = linear(_layernorm(q1, ca.q_proj[0]), self._w(ca.q_proj[1]))
+            for t, (lat, n, off) in enumerate(zip(latents, (n0, n1), (0, rows0))):
+                pos = getattr(layer, f"pos_embed_{t}", None)
+                kw = dict(resid=None if pos is None else pos.detach().float().contiguous(),
+                          resid_period=0 if pos is None else n)
+                kp, vp = getattr(ca, f"k_proj_{t}"), getattr(ca, f"v_proj_{t}")
+                linear(_layernorm(lat, kp[0], **kw), self._w(kp[1]), out=kbuf[off:off + R * n])
+                linear(_layernorm(lat, vp[0], **kw), self._w(vp[1]), out=vbuf[off:off + R * n])
+            with torch.cuda.device(dev):
+                rc = lib.tdc_attention(_ptr(qs), _ptr(kbuf), _ptr(vbuf), _ptr(att), H, H, H, H, R, H // 64, 1, 0, 0, 0,
+                                       n0, n1, 0, rows0, None, _ptr(mask), _stream(dev))
+            _lib.check(rc, None, "tdc_attention")
+            o = linear(att, self._w(ca.o_proj), out_dtype=torch.float32)
+            q2 = _layernorm(o, layer.norm, resid=q1)                             # norm(queries + attention_output)
+            m = linear(linear(q2, self._w(layer.proj_out.linear_1), gelu=True), self._w(layer.proj_out.linear_2),
+                       out_dtype=torch.float32)
+            new32 = torch.empty_like(q32)
+            new16 = torch.empty_like(q16)
+            with torch.cuda.device(dev):
+                rc = lib.tdc_residual_add(_ptr(m), _ptr(q32), _ptr(new32), _ptr(new16), m.numel(), _stream(dev))
+            _lib.check(rc, None, "tdc_residual_add")
+            q32, q16 = new32, new16
+        return q16.view(bs, Q * Q, H)

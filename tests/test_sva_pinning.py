@@ -1,0 +1,79 @@
+"""Pin the SVA oracle (oracle/sva_oracle.py) against the reference's own modules, loaded unmodified
+(tdc/vision_sampler.py imports only torch/numpy) and against the real window rearrangement.  Build container only."""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shim, sva_oracle
+from oracle.synth import make_sva_state_dict
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not present")
+
+
+def _load_vision_sampler():
+    name = "_tdc_reference_vision_sampler"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ref_shim.REFERENCE_ROOT, "tdc", "vision_sampler.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("hidden,sides,layers,sizes", [
+    (128, (2, 2), 2, [(384, 384), (384, 384)]),
+    (128, (2, 1), 1, [(640, 360), (384, 384), (300, 500)]),     # letterboxed / pillarboxed frames -> real masks
+    (256, (2, 2), 3, [(1280, 720)]),
+])
+def test_token_sampler_and_projector_equal_reference(hidden, sides, layers, sizes):
+    vs = _load_vision_sampler()
+    tower_dims = (96, 64)
+    Q = 4                                             # query grid side (12 in the shipped config)
+    sd = make_sva_state_dict(hidden, tower_dims, sides, layers, seed=hidden + layers, stress=3.0)
+    bs = len(sizes)
+    rs = np.random.RandomState(1)
+    tower = [torch.from_numpy(rs.standard_normal((bs, (Q * s) ** 2, c)).astype(np.float32))
+             for s, c in zip(sides, tower_dims)]
+
+    # --- reference modules
+    sampler = vs.VisionTokenSampler(hidden, hidden, [hidden] * 2, list(sides), hidden, layers).eval()
+    own = {k[len("vision_sampler_0."):]: torch.from_numpy(v) for k, v in sd.items() if k.startswith("vision_sampler_0.")}
+    sampler.load_state_dict(own, strict=True)
+    proj = []
+    for t, c in enumerate(tower_dims):
+        m = torch.nn.Sequential(torch.nn.Linear(c, hidden), torch.nn.GELU(), torch.nn.Linear(hidden, hidden),
+                                torch.nn.LayerNorm(hidden)).eval()
+        m.load_state_dict({k[len(f"mm_projector_aux_{t}."):]: torch.from_numpy(v) for k, v in sd.items()
+                           if k.startswith(f"mm_projector_aux_{t}.")}, strict=True)
+        proj.append(m)
+    from oracle import harness
+    arch = harness._load_cambrian_arch()
+
+    class Bare(arch.CambrianMetaForCausalLM):
+        def get_model(self):
+            return None
+
+    with torch.no_grad():
+        feats = [proj[t](tower[t]) for t in range(2)]
+        lat, masks = Bare().rearrange_vision_tower_features_inference(feats, Q, sizes)
+        nq = Q * Q
+        ctx = feats[0].mean(1).view(bs, 1, 1, -1).expand(-1, nq, 1, -1).flatten(0, 1)
+        qry = torch.from_numpy(sd["vision_query"])[0].view(1, 1, 1, -1).expand(bs, nq, -1, -1).flatten(0, 1)
+        masks_r = [m.view(m.shape[0], 1, 1, -1).expand(-1, -1, 1, -1) for m in masks]   # as VisionCrossAttentionLayer does
+        ref = sampler(qry, ctx, *lat, *masks).view(bs, nq, hidden)
+
+    # pieces
+    for t in range(2):
+        assert torch.allclose(sva_oracle.mm_projector_aux(sd, f"mm_projector_aux_{t}", tower[t]), feats[t], atol=1e-5)
+        assert torch.equal(sva_oracle.rearrange_windows(feats[t], Q), lat[t])
+        grid = Q * sides[t]
+        m = torch.cat([sva_oracle.window_masks(sizes[b], grid, Q) for b in range(bs)], 0)
+        assert torch.equal(m, masks[t])
+    got = sva_oracle.sva_frames(sd, tower, sizes, Q, layers)
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 5e-5
