@@ -46,16 +46,33 @@ WORKLOADS = {
     # BASELINE.json config 2: 256 segments, Llama-3.2-3B widths
     "cfg2_llama3b": dict(segments=256, frames_per_segment=4, kv_tokens=206, audio_tokens=50, d_enc=3072, d_out=3072,
                          num_query=16, num_text=0, label="256-segment video, Llama-3.2-3B widths (d=3072), L=206, K=16"),
+    # ---- variants of SURVEY.md 8.0 / 8d (not the driver's line; run with --workload) -------------------------------
+    # BASELINE-literal order: Q-Former on the towers' own width (SigLIP d=1152, 144 visual + 50 audio tokens), then
+    # the GELU-MLP projector 768 -> d_llm instead of vision_proj + normalise
+    "literal_d1152_mlp": dict(segments=3600, frames_per_segment=4, kv_tokens=194, audio_tokens=50, d_enc=1152,
+                              d_out=3584, num_query=16, num_text=0, projector="gelu_mlp",
+                              label="1-hour video, BASELINE-literal order: Q-Former at d_enc=1152, L=194, then "
+                                    "GELU-MLP projector 768->3584"),
+    # north-star reading "segment KV": every row attends to all F*144 + 50 tokens of its segment
+    "segment_kv_d1152": dict(segments=3600, frames_per_segment=4, kv_tokens=626, audio_tokens=50, d_enc=1152,
+                             d_out=3584, num_query=16, num_text=0,
+                             label="1-hour video, segment-level KV (L = 4*144 + 50 = 626), d_enc=1152"),
+    # BASELINE.json config 5: 64 concurrent 10-minute videos = 38 400 segments over 8 GPUs -> 4800 per GPU
+    # (K = 16 default; --num-query 64 for the sweep)
+    "eval64x600": dict(segments=4800, frames_per_segment=4, kv_tokens=206, audio_tokens=50, d_enc=3584, d_out=3584,
+                       num_query=16, num_text=0,
+                       label="64 x 10-minute videos over 8 GPUs (4800 segments per GPU), Qwen2-7B widths, L=206"),
 }
 H, I, LAYERS, HEADS, N_CROSS = 768, 3072, 12, 12, 6
 
 
-def flops_per_row(L, d_enc, K, T, d_out):
+def flops_per_row(L, d_enc, K, T, d_out, projector="vision_proj"):
     """Algorithmic FLOPs of one row, reference formulation."""
     n = K + T
     kv = N_CROSS * 2 * (2 * L * d_enc * H)
+    proj = 2 * K * H * d_out if projector == "vision_proj" else 2 * K * (H * d_out + d_out * d_out)
     rest = (LAYERS * (8 * n * H * H + 4 * n * n * H) + N_CROSS * (4 * K * H * H + 4 * K * L * H)
-            + LAYERS * 4 * K * H * I + LAYERS * 4 * T * H * I + 2 * K * H * d_out)
+            + LAYERS * 4 * K * H * I + LAYERS * 4 * T * H * I + proj)
     return kv + rest, kv
 
 
@@ -150,6 +167,13 @@ def build_problem(w, seed):
     T = w.get("num_text", 0)
     geom = QFormerGeometry(d_enc=w["d_enc"], d_out=w["d_out"], vocab=30522 if T else 0)
     sd = make_state_dict(geom, seed, with_text=T > 0)
+    if w.get("projector") == "gelu_mlp":   # mm_projector-style Sequential: `0.*` Linear(768 -> d), `2.*` Linear(d -> d)
+        rs = np.random.RandomState(seed + 17)
+        d = w["d_out"]
+        sd["mm_projector.0.weight"] = (rs.standard_normal((d, geom.hidden)) * 0.02).astype(np.float32)
+        sd["mm_projector.0.bias"] = (rs.standard_normal(d) * 0.02).astype(np.float32)
+        sd["mm_projector.2.weight"] = (rs.standard_normal((d, d)) * 0.02).astype(np.float32)
+        sd["mm_projector.2.bias"] = (rs.standard_normal(d) * 0.02).astype(np.float32)
     rows = w["segments"] * (w["frames_per_segment"] - 1)
     return geom, sd, rows
 
@@ -165,10 +189,18 @@ def cpu_baseline(geom, sd, w, sample_rows, seed):
     inp = make_inputs(geom, seed, sample_rows, w["kv_tokens"], w["num_query"], T, audio_tokens=w["audio_tokens"])
     ids = None if T == 0 else np.repeat(inp["input_ids"][:1], sample_rows, axis=0)   # one prompt for the whole video
     sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
+    if w.get("projector") == "gelu_mlp":
+        def run(q, e, i):
+            h = oracle.qformer_forward(sd_t, geom, q, e, i)[:, :w["num_query"]]
+            return oracle.gelu_mlp(sd_t["mm_projector.0.weight"], sd_t["mm_projector.0.bias"],
+                                   sd_t["mm_projector.2.weight"], sd_t["mm_projector.2.bias"], h)
+    else:
+        def run(q, e, i):
+            return oracle.compress(sd_t, geom, q, e, i)
     with torch.no_grad():
-        oracle.compress(sd_t, geom, inp["query_embeds"][:2], inp["enc"][:2], None if ids is None else ids[:2])  # warm-up
+        run(inp["query_embeds"][:2], inp["enc"][:2], None if ids is None else ids[:2])  # warm-up
         t0 = time.perf_counter()
-        oracle.compress(sd_t, geom, inp["query_embeds"], inp["enc"], ids)
+        run(inp["query_embeds"], inp["enc"], ids)
         dt = time.perf_counter() - t0
     rows_per_s = sample_rows / dt
     return rows_per_s / (w["frames_per_segment"] - 1), dt, cores
@@ -215,6 +247,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cta-group", type=int, default=0)
+    ap.add_argument("--num-query", type=int, default=0, help="override K (BASELINE config 5 sweeps K = 16 and 64)")
     ap.add_argument("--num-text", type=int, default=0, help="prompt tokens T shared by all rows (text_input mode; default 0 = north-star)")
     ap.add_argument("--gather-batches", type=int, default=2, help="row batches per step at N > 1 (comm/compute overlap)")
     ap.add_argument("--no-multicast", action="store_true", help="N > 1: use the NCCL all-gather instead of multicast stores")
@@ -223,6 +256,9 @@ def main():
     if args.segments:
         w["segments"] = args.segments
     w["num_text"] = args.num_text
+    if args.num_query:
+        w["num_query"] = args.num_query
+    w.setdefault("projector", "vision_proj")
     if args.impl == "reference":
         return run_reference_arm(args, w)
 
@@ -247,7 +283,21 @@ def main():
     S = w["segments"]
     T = w["num_text"]
     eng = QFormerEngine(d_enc=d_enc, d_out=d_out, vocab=30522 if T else 0, device=dev, gemm_cta_group=args.cta_group)
-    eng.load_weights(sd)
+    eng.load_weights({k: v for k, v in sd.items() if not k.startswith("mm_projector.")})
+    mlp = None
+    if w["projector"] == "gelu_mlp":
+        from tdc_video_b200.projector import gelu_mlp
+        mlp = [torch.from_numpy(sd[f"mm_projector.{i}.{p}"]).to(dev, torch.bfloat16 if p == "weight" else torch.float32)
+               for i in (0, 2) for p in ("weight", "bias")]
+        args.no_e2e = True          # compress_host streams the vision_proj flavour only
+        args.no_multicast = True
+
+    def compute(enc_rows, qs_rows, ts_rows):
+        """One pass of the hot path over a row range: Q-Former + projector flavour of the workload."""
+        if mlp is None:
+            return eng.compress(q_dev, enc_rows, ids_dev, query_set=qs_rows, text_set=ts_rows, out_dtype=torch.bfloat16)
+        hidden = eng.forward(q_dev, enc_rows, ids_dev, query_set=qs_rows, text_set=ts_rows, out_dtype=torch.bfloat16)
+        return gelu_mlp(hidden[:, :K], *mlp)
 
     # ---- synthetic inputs, generated on the host in pinned memory (also the e2e source), then made resident
     # (values are drawn with the device RNG for speed — 8e9 normals — then the HOST copy is the
@@ -294,7 +344,7 @@ def main():
 
     def step():
         if world == 1:
-            return eng.compress(q_dev, enc, ids_dev, query_set=qs_dev, text_set=ts_dev, out_dtype=torch.bfloat16)
+            return compute(enc, qs_dev, ts_dev)
         # the path's one exchange step: all-gather of the compressed tokens, issued per row batch on
         # NCCL's stream so that it overlaps the next batch's kernels; every rank ends with the
         # rank-ordered sequence [world, rows, K, d_out]
@@ -308,8 +358,7 @@ def main():
             return mcast.gathered
         works = []
         for r0, r1 in bounds:
-            out = eng.compress(q_dev, enc[r0:r1], ids_dev, query_set=qs_dev[r0:r1],
-                               text_set=None if ts_dev is None else ts_dev[r0:r1], out_dtype=torch.bfloat16)
+            out = compute(enc[r0:r1], qs_dev[r0:r1], None if ts_dev is None else ts_dev[r0:r1])
             works.append(dist.all_gather([gathered[w, r0:r1] for w in range(world)], out, async_op=True))
         for wk in works:
             wk.wait()
@@ -355,6 +404,8 @@ def main():
         e2e_kw = dict(query_set=query_set, rows_per_batch=args.e2e_rows_per_batch,
                       input_ids=None if ids_dev is None else ids_dev.cpu(),
                       text_set=None if ts_dev is None else ts_dev.cpu())
+        if world > 1:   # the rank's own rows stay on the GPU too: send buffer of the exchange
+            e2e_kw["out_device"] = torch.empty((rows, K, d_out), dtype=torch.bfloat16, device=dev)
         eng.compress_host(q_sets, enc_host, out_host, **e2e_kw)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -362,7 +413,7 @@ def main():
         for _ in range(args.e2e_steps):
             eng.compress_host(q_sets, enc_host, out_host, **e2e_kw)
             if world > 1:
-                dist.all_gather_into_tensor(gathered.view(world * rows, K, d_out), out_host.to(dev, non_blocking=True))
+                dist.all_gather_into_tensor(gathered.view(world * rows, K, d_out), e2e_kw["out_device"])
                 # (e2e keeps the plain NCCL exchange: the result is read back to the host per batch anyway)
         e1.record()
         barrier()
@@ -381,7 +432,7 @@ def main():
         return
 
     peaks = measured_peaks()
-    f_row, f_row_kv = flops_per_row(L, d_enc, K, T, d_out)
+    f_row, f_row_kv = flops_per_row(L, d_enc, K, T, d_out, w["projector"])
     kv_ms, kv_n = prof["kv_gemm"]["ms"], prof["kv_gemm"]["launches"]
     kv_flops_per_launch = f_row_kv * rows * args.steps / max(kv_n, 1)
     kv_achieved = kv_flops_per_launch / (kv_ms / max(kv_n, 1) * 1e-3) / 1e12 if kv_ms > 0 else None
@@ -391,7 +442,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["label"], "segments_per_gpu": S, "rows_per_gpu": rows,
-                   "kv_tokens": L, "d_enc": d_enc, "d_out": d_out, "num_query": K, "num_text": T,
+                   "kv_tokens": L, "d_enc": d_enc, "d_out": d_out, "num_query": K, "num_text": T, "projector": w["projector"],
                    "parallelism": f"dp{world} (video-second ranges per GPU)", "exchange": exchange,
                    "l2": f"inputs {enc.numel() * 2 / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
                    "accumulate": "fp32 (TMEM), LN/softmax/residual fp32"},

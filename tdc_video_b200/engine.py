@@ -163,11 +163,13 @@ class QFormerEngine:
 
     def compress_host(self, query_embeds: torch.Tensor, enc_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
                       *, query_set: Optional[torch.Tensor] = None, input_ids: Optional[torch.Tensor] = None,
-                      text_set: Optional[torch.Tensor] = None, rows_per_batch: int = 1024) -> torch.Tensor:
+                      text_set: Optional[torch.Tensor] = None, rows_per_batch: int = 1024,
+                      out_device: Optional[torch.Tensor] = None) -> torch.Tensor:
         """`compress` for inputs that live in (pinned) HOST memory: enc_host [rows, L, d_enc] is streamed
         to the GPU in row batches on a copy stream while the previous batch computes, and each batch's
         [n, K, d_out] result is copied back to `out_host` on a third stream.  Stream-ordered: the
-        result is complete once the current stream is synchronised."""
+        result is complete once the current stream is synchronised.  `out_device` [rows, K, d_out], if
+        given, additionally keeps the result on the GPU (e.g. as the send buffer of the all-gather)."""
         rows, L, _ = enc_host.shape
         K = query_embeds.shape[1]
         dev = self.device
@@ -199,6 +201,8 @@ class QFormerEngine:
                                     ids_dev if (ids_dev is None or ts_dev is not None) else ids_dev[r0:r1],
                                     query_set=None if qs_dev is None else qs_dev[r0:r1],
                                     text_set=None if ts_dev is None else ts_dev[r0:r1], out_dtype=out_host.dtype)
+            if out_device is not None:
+                out_device[r0:r1].copy_(out_dev)
             compute_done[b].record(cur)
             with torch.cuda.stream(self._d2h_stream):
                 self._d2h_stream.wait_event(compute_done[b])

@@ -143,6 +143,25 @@ class SVAConnector(nn.Module):
             self._bf16[key] = lin.weight.detach().to(torch.bfloat16).contiguous()
         return self._bf16[key]
 
+    def _kv_folded(self, li: int, t: int):
+        """K and V projections of one tower as ONE GEMM over the shared normalised input: both are
+        Linear(LayerNorm(x)) of the same x (vision_sampler.py:192-217), and LayerNorm(x) = xhat * gamma + beta with
+        xhat = (x - mean) / std common to the two, so W (gamma * xhat + beta) = (W diag(gamma)) xhat + W beta.
+        Returns ([2H, H] bf16 weight, [2H] fp32 bias, ones/zeros LayerNorm parameters); made once."""
+        key = ("kv", li, t)
+        if key not in self._bf16:
+            ca = self.vision_sampler_0.layers[li].cross_attn
+            ws, bs = [], []
+            for name in (f"k_proj_{t}", f"v_proj_{t}"):
+                ln, lin = getattr(ca, name)
+                w = lin.weight.detach().float()
+                ws.append(w * ln.weight.detach().float()[None, :])
+                bs.append(w @ ln.bias.detach().float())
+            dev = ws[0].device
+            self._bf16[key] = (torch.cat(ws, 0).to(torch.bfloat16).contiguous(), torch.cat(bs, 0).contiguous(),
+                               torch.ones(self.hidden, device=dev), torch.zeros(self.hidden, device=dev))
+        return self._bf16[key]
+
     @torch.no_grad()
     def forward(self, tower_feats: Sequence[torch.Tensor], image_sizes: Sequence[Tuple[int, int]]) -> torch.Tensor:
         """tower_feats[t]: [bs, grid_t^2, C_t] (CUDA); image_sizes[b] = (width, height) of frame b before padding.
@@ -178,10 +197,10 @@ class SVAConnector(nn.Module):
         mask = torch.from_numpy(window_mask_bits(image_sizes, grids, Q).view(np.int32)).to(dev)
         n0, n1 = self.window_sides[0] ** 2, self.window_sides[1] ** 2
         rows0 = R * n0                                                           # K/V rows of tower 0 precede tower 1's
-        kbuf = torch.empty((R * (n0 + n1), H), dtype=torch.bfloat16, device=dev)
-        vbuf = torch.empty_like(kbuf)
+        kv = torch.empty((R * (n0 + n1), 2 * H), dtype=torch.bfloat16, device=dev)   # row = [K | V] of one token
+        xhat = torch.empty((R * max(n0, n1), H), dtype=torch.bfloat16, device=dev)
         att = torch.empty((R, H), dtype=torch.bfloat16, device=dev)
-        for layer in self.vision_sampler_0.layers:
+        for li, layer in enumerate(self.vision_sampler_0.layers):
             ca = layer.cross_attn
             # proj_context + cat + proj_in (vision_sampler.py:346-360); the context is one vector per frame
             ctx = linear(context, self._w(layer.proj_context))                   # [bs, H] bf16
@@ -190,14 +209,19 @@ class SVAConnector(nn.Module):
             qs = linear(_layernorm(q1, ca.q_proj[0]), self._w(ca.q_proj[1]))
             for t, (lat, n, off) in enumerate(zip(latents, (n0, n1), (0, rows0))):
                 pos = getattr(layer, f"pos_embed_{t}", None)
-                kw = dict(resid=None if pos is None else pos.detach().float().contiguous(),
-                          resid_period=0 if pos is None else n)
-                kp, vp = getattr(ca, f"k_proj_{t}"), getattr(ca, f"v_proj_{t}")
-                linear(_layernorm(lat, kp[0], **kw), self._w(kp[1]), out=kbuf[off:off + R * n])
-                linear(_layernorm(lat, vp[0], **kw), self._w(vp[1]), out=vbuf[off:off + R * n])
+                w_kv, b_kv, ones, zeros = self._kv_folded(li, t)
+                # one normalisation pass (statistics only) shared by K and V, then one N = 2H GEMM
+                with torch.cuda.device(dev):
+                    rc = lib.tdc_layernorm(_ptr(lat), None if pos is None else _ptr(pos.detach().float().contiguous()),
+                                           0 if pos is None else n, _ptr(ones), _ptr(zeros),
+                                           float(getattr(ca, f"k_proj_{t}")[0].eps), None,
+                                           _ptr(xhat), R * n, H, _stream(dev))
+                _lib.check(rc, None, "tdc_layernorm")
+                linear(xhat[:R * n], w_kv, b_kv, out=kv[off:off + R * n])
             with torch.cuda.device(dev):
-                rc = lib.tdc_attention(_ptr(qs), _ptr(kbuf), _ptr(vbuf), _ptr(att), H, H, H, H, R, H // 64, 1, 0, 0, 0,
-                                       n0, n1, 0, rows0, None, _ptr(mask), _stream(dev))
+                rc = lib.tdc_attention(_ptr(qs), _ptr(kv), C.c_void_p(kv.data_ptr() + H * kv.element_size()), _ptr(att), H, 2 * H,
+                                       2 * H, H, R, H // 64, 1, 0, 0, 0, n0, n1, 0, rows0, None, _ptr(mask),
+                                       _stream(dev))
             _lib.check(rc, None, "tdc_attention")
             o = linear(att, self._w(ca.o_proj), out_dtype=torch.float32)
             q2 = _layernorm(o, layer.norm, resid=q1)                             # norm(queries + attention_output)

@@ -73,6 +73,28 @@ def test_row_batching_is_invisible():
     _check(full, ref, "batched/compressed")
 
 
+def test_compress_host_streams_the_same_bits():
+    """The end-to-end entry (KV tokens in pinned host memory, row batches over three streams) is the same
+    computation as the resident call: identical bits, ragged last batch, optional on-device copy."""
+    geom = QFormerGeometry(hidden=128, heads=2, intermediate=256, layers=2, cross_freq=2, d_enc=64, d_out=64, vocab=0)
+    sd = make_state_dict(geom, 15, with_text=False)
+    inp = make_inputs(geom, 16, rows=23, kv_tokens=29, num_query=16)
+    eng = _engine(geom, sd)
+    qsets = torch.from_numpy(inp["query_embeds"][:8])
+    qmap = (torch.arange(23) // 3).to(torch.int32)
+    enc_host = torch.from_numpy(inp["enc"]).bfloat16().pin_memory()
+    resident = eng.compress(qsets.cuda(), enc_host.cuda(), query_set=qmap.cuda())
+    keep = torch.zeros((23, 16, 64), dtype=torch.bfloat16, device="cuda")
+    for rb in (5, 23, 1000):
+        keep.zero_()
+        out_host = eng.compress_host(qsets, enc_host, query_set=qmap, rows_per_batch=rb, out_device=keep)
+        torch.cuda.synchronize()
+        assert out_host.is_pinned() and torch.equal(out_host, resident.cpu()), rb
+        assert torch.equal(keep, resident), rb
+    ref = oracle.compress(sd, geom, qsets[qmap.long()], enc_host.float())
+    _check(out_host, ref, "host-streamed/compressed")
+
+
 def test_query_set_broadcast_and_shared_text():
     """All rows of a chunk share queries and prompt (cambrian_arch.py:1629-1646): the index maps
     must equal materialised expansion."""
