@@ -17,7 +17,7 @@ NCCL all-gather of the compressed tokens so that every rank holds the ordered se
               FLOPs / its CUDA-event time (events on the launching stream, recorded by the library)
  * `cpu_baseline`: the reference algorithm (oracle port, fp32 torch) on the host cores, bounded sample
 
-Synthetic data, random-init weights (oracle/synth.py statistics); weak scaling: every GPU
+Synthetic data, random-init weights (tdc_video_b200/synth.py statistics); weak scaling: every GPU
 compresses its own `segments` video-seconds.
 """
 from __future__ import annotations
@@ -163,7 +163,7 @@ def bind_to_gpu_numa_node(index):
 def build_problem(w, seed):
     """Synthetic video of the workload: per-row KV tokens, one query set per segment (Avg_pool-style:
     all rows of a segment share the queries derived from its static frame)."""
-    from oracle.synth import QFormerGeometry, make_state_dict
+    from tdc_video_b200.synth import QFormerGeometry, make_state_dict
     T = w.get("num_text", 0)
     geom = QFormerGeometry(d_enc=w["d_enc"], d_out=w["d_out"], vocab=30522 if T else 0)
     sd = make_state_dict(geom, seed, with_text=T > 0)
@@ -182,7 +182,7 @@ def cpu_baseline(geom, sd, w, sample_rows, seed):
     """The reference algorithm (oracle port of tdc/Qformer.py + vision_proj + normalize), fp32 torch on
     all host cores, batched as ONE call (kinder to the CPU than the reference's <= 7-row loop)."""
     from oracle import qformer_oracle as oracle
-    from oracle.synth import make_inputs
+    from tdc_video_b200.synth import make_inputs
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     T = w.get("num_text", 0)

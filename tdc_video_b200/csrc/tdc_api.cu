@@ -368,6 +368,12 @@ int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long
 
   for (int l = 0; l < c.layers; ++l) {
     const LayerW& lw = h->layers[l];
+    // tdc_compress reads only the query tokens of the last layer (cambrian_arch.py:1665 `[:, :K]`): there the
+    // text tokens still feed the queries' self-attention as keys / values, but their own attention output,
+    // out-projection, LayerNorms and feed-forward are dead and are skipped (the query tokens' bits do not change).
+    const bool text_live = T > 0 && !(f.compress && l == c.layers - 1);
+    const int nq_self = text_live ? n : K;
+    const long long M_self = text_live ? MA : MQ;
     // ---- self-attention over all K+T tokens of the row
     TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16, H, lw.w_qkv, H, lw.b_qkv, w.qkv, 3 * H, MA, 3 * H, H,
                  EPI_BIAS_BF16, &err));
@@ -375,15 +381,15 @@ int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long
       AttentionArgs a;
       a.q = w.qkv; a.k = w.qkv + H; a.v = w.qkv + 2 * H; a.out = w.ctx;
       a.ldq = a.ldk = a.ldv = 3 * H; a.ldo = H;
-      a.rows = static_cast<int>(rows); a.heads = c.heads; a.nq = n;
-      a.q_seg1 = K; a.q_seg2 = T; a.q_base1 = 0; a.q_base2 = MQ;
+      a.rows = static_cast<int>(rows); a.heads = c.heads; a.nq = nq_self;
+      a.q_seg1 = K; a.q_seg2 = text_live ? T : 0; a.q_base1 = 0; a.q_base2 = MQ;
       a.kv_seg1 = K; a.kv_seg2 = T; a.kv_base1 = 0; a.kv_base2 = MQ;
       a.scale_log2 = scale_log2;
       KernelScope ks(h, TDC_K_ATTENTION, s);
       TDC_TRY(attention_launch(a, s, &err));
     }
-    TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.ctx, H, lw.w_ao, H, lw.b_ao, w.pre, H, MA, H, H, EPI_BIAS_F32, &err));
-    TDC_TRY(ln(lw.ln_a_g, lw.ln_a_b, 0, MA));
+    TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.ctx, H, lw.w_ao, H, lw.b_ao, w.pre, H, M_self, H, H, EPI_BIAS_F32, &err));
+    TDC_TRY(ln(lw.ln_a_g, lw.ln_a_b, 0, M_self));
 
     // ---- cross-attention: query tokens only
     if (lw.cross_index >= 0) {
@@ -412,7 +418,7 @@ int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long
                  &err));
     TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.mid, I, lw.w_fq2, I, lw.b_fq2, w.pre, H, MQ, H, I, EPI_BIAS_F32, &err));
     TDC_TRY(ln(lw.ln_fq_g, lw.ln_fq_b, 0, MQ));
-    if (T > 0) {
+    if (text_live) {
       TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16 + MQ * H, H, lw.w_ft1, H, lw.b_ft1, w.mid, I, MT, I, H,
                    EPI_BIAS_GELU_BF16, &err));
       TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.mid, I, lw.w_ft2, I, lw.b_ft2, w.pre + MQ * H, H, MT, H, I,

@@ -9,7 +9,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import sva_oracle  # noqa: E402  (checker + CPU baseline only)
-from oracle.synth import make_sva_state_dict  # noqa: E402
+from tdc_video_b200.synth import make_sva_state_dict  # noqa: E402
 from tdc_video_b200.sva import SVAConnector  # noqa: E402
 
 

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle.synth import QFormerGeometry, make_state_dict  # noqa: E402
+from tdc_video_b200.synth import QFormerGeometry, make_state_dict  # noqa: E402
 from tdc_video_b200 import QFormerEngine  # noqa: E402
 from tdc_video_b200.dist import MulticastGather  # noqa: E402
 
