@@ -74,11 +74,33 @@ def run_reference(geom, sd_np, inputs, num_query, kv_len=None):
 DRIVER_D = 48
 DRIVER_GEOM = QFormerGeometry(hidden=64, heads=1, intermediate=96, layers=2, cross_freq=2, d_enc=DRIVER_D,
                               d_out=DRIVER_D, vocab=40, max_pos=16)
-# name -> (n_frames, K, query_type, text, add_static, tokenizer_model_max_length)
+# name -> (n_frames, K, query_type, text, add_static, tokenizer_model_max_length, audio pattern or None)
 DRIVER_CASES = {
-    "avgpool_text_33f": (33, 8, "Avg_pool", True, True, 100000),
-    "learned_notext_budget_30f": (30, 8, "learned", False, True, 2600),
+    "avgpool_text_33f": (33, 8, "Avg_pool", True, True, 100000, None),
+    "learned_notext_budget_30f": (30, 8, "learned", False, True, 2600, None),
+    "avgpool_text_audio_sparse_27f": (27, 8, "Avg_pool", True, True, 100000, "sparse"),
 }
+
+
+def driver_audio(seed, n_frames, pattern):
+    """Stub BEATs output for the audio branch (cambrian_arch.py:1547-1598): per 10-second window a [1, t, 768]
+    feature block (the last one 7 tokens short), the 0/1 "second was sampled" flags and `audio_proj` weights.
+    "sparse": a 61-second clip of which n_frames seconds were sampled, with gaps of 1-4 seconds."""
+    rs = np.random.RandomState(seed)
+    if pattern == "every_second":
+        seconds, flags = n_frames, [1] * n_frames
+    else:
+        seconds = 61
+        pos = set(np.sort(rs.choice(seconds, size=n_frames, replace=False)).tolist())
+        flags = [1 if i in pos else 0 for i in range(seconds)]
+    n_win = (seconds + 9) // 10
+    windows = []
+    for w in range(n_win):
+        secs_w = min(10, seconds - 10 * w)
+        windows.append(rs.standard_normal((1, secs_w * 50 - (7 if w == n_win - 1 else 0), 768)).astype(np.float32))
+    proj = {"audio_proj.weight": (rs.standard_normal((DRIVER_D, 768)) * 0.05).astype(np.float32),
+            "audio_proj.bias": (rs.standard_normal((DRIVER_D,)) * 0.05).astype(np.float32)}
+    return windows, flags, seconds, proj
 
 
 def driver_weights(seed, K):
@@ -115,18 +137,23 @@ def driver_frames(w, sig, dino):
 
 def make_driver_goldens(only=None):
     from oracle import harness
-    for name, (n, K, qt, text, static, max_len) in DRIVER_CASES.items():
+    for name, (n, K, qt, text, static, max_len, audio) in DRIVER_CASES.items():
         if only and name not in only:
             continue
         w = driver_weights(40 + n, K)
         sig, dino = driver_tables(50 + n, n)
+        akw = {}
+        if audio:
+            windows, flags, seconds, proj = driver_audio(60 + n, n, audio)
+            w.update(proj)
+            akw = dict(audio_windows=windows, video_indices=torch.tensor(flags, dtype=torch.int16), audio_seconds=seconds)
         ref = harness.run_reference_driver(w, DRIVER_GEOM, n, d_llm=DRIVER_D, context_token_num=K, query_type=qt,
                                            text_input=text, add_static=static, tokenizer_model_max_length=max_len,
-                                           prompt_ids=[[3, 9, 4, 1]], siglip_table=sig, dino_table=dino)
+                                           prompt_ids=[[3, 9, 4, 1]], siglip_table=sig, dino_table=dino, **akw)
         assert torch.allclose(ref["frames"], driver_frames(w, sig, dino), atol=1e-6)
         meta = dict(n_frames=n, num_query=K, query_type=qt, text=text, add_static=static,
                     tokenizer_model_max_length=max_len, max_visual_len=max_len - 16 - 3, prompt_ids=[3, 9, 4, 1],
-                    weight_seed=40 + n, table_seed=50 + n,
+                    weight_seed=40 + n, table_seed=50 + n, audio=audio, audio_seed=60 + n,
                     generator="oracle/make_golden.py: reference prepare_inputs_labels_for_multimodal via oracle/harness.py")
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"driver_{name}.npz"), meta=json.dumps(meta),
                             segment_frame_indices=ref["segment_frame_indices"].numpy().astype(np.int64),

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle import driver_oracle
-from oracle.make_golden import DRIVER_GEOM, driver_frames, driver_tables, driver_weights
+from oracle.make_golden import DRIVER_GEOM, driver_audio, driver_frames, driver_tables, driver_weights
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "driver_*.npz")))
 
@@ -23,12 +23,18 @@ def test_driver_oracle_matches_reference_golden(path):
     sig, dino = driver_tables(m["table_seed"], m["n_frames"])
     frames = driver_frames(w, sig, dino)
     sizes = driver_oracle.segment_sizes_from_boundaries(z["segment_frame_indices"], m["n_frames"])
+    audio_frames = None
+    if m.get("audio"):
+        windows, flags, _, proj = driver_audio(m["audio_seed"], m["n_frames"], m["audio"])
+        w.update(proj)
+        audio_frames = driver_oracle.audio_frames_from_beats(windows, flags, m["n_frames"])
     got = driver_oracle.compress_video(w, DRIVER_GEOM, frames, sizes, context_token_num=m["num_query"],
                                        query_type=m["query_type"], add_text=m["text"], keep_static=m["add_static"],
-                                       input_ids=torch.tensor([m["prompt_ids"]]), max_visual_len=m["max_visual_len"])
+                                       input_ids=torch.tensor([m["prompt_ids"]]), max_visual_len=m["max_visual_len"],
+                                       audio_frames=audio_frames)
     assert got.shape == z["visual_tokens"].shape
     assert float(np.abs(got.numpy() - z["visual_tokens"]).max()) <= 2e-5
 
 
 def test_driver_goldens_exist():
-    assert len(GOLDEN) >= 2
+    assert len(GOLDEN) >= 3

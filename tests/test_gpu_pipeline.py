@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from oracle import qformer_oracle as oracle
-from oracle.make_golden import DRIVER_D, DRIVER_GEOM, driver_frames, driver_tables, driver_weights
+from oracle.make_golden import DRIVER_D, DRIVER_GEOM, driver_audio, driver_frames, driver_tables, driver_weights
 
 pytestmark = pytest.mark.gpu
 
@@ -27,12 +27,12 @@ def _compressor(m, w):
                         max_position_embeddings=g.max_pos, layer_norm_eps=g.ln_eps,
                         cross_attention_freq=g.cross_freq, encoder_width=DRIVER_D, query_length=m["num_query"])
     comp = TDCCompressor(DRIVER_D, context_token_num=m["num_query"], query_type=m["query_type"], text_input=m["text"],
-                         add_static=m["add_static"], qformer_config=cfg)
+                         add_static=m["add_static"], audio_input=bool(m.get("audio")), qformer_config=cfg)
     sd = {}
     for k, v in w.items():
         if k.startswith(("embeddings.", "encoder.")):
             sd["Qformer.bert." + k] = torch.from_numpy(v)
-        elif k.split(".")[0] in ("vision_proj", "query_proj", "frame_seg", "query_tokens"):
+        elif k.split(".")[0] in ("vision_proj", "query_proj", "frame_seg", "query_tokens", "audio_proj"):
             sd[k] = torch.from_numpy(v)
     missing, unexpected = comp.load_state_dict(sd, strict=False)
     assert not unexpected, unexpected
@@ -49,6 +49,11 @@ def test_stage_matches_the_reference_driver(path):
     w = driver_weights(m["weight_seed"], m["num_query"])
     sig, dino = driver_tables(m["table_seed"], m["n_frames"])
     n = m["n_frames"]
+    audio_kw = {}
+    if m.get("audio"):   # stub BEATs windows + sampled-second flags: the audio branch (cambrian_arch.py:1547-1614)
+        windows, flags, _, proj = driver_audio(m["audio_seed"], n, m["audio"])
+        w.update(proj)
+        audio_kw = dict(audio_windows=[torch.from_numpy(a).cuda() for a in windows], sample_indices=flags)
     # frame tokens: mm_projector on the concatenated tower features (tcgen05 GEMM), then the newline column
     feats = torch.from_numpy(np.concatenate([sig, dino], -1)).cuda()
     proj = linear(feats, torch.from_numpy(w["mm_projector.weight"]).cuda(), torch.from_numpy(w["mm_projector.bias"]).cuda(),
@@ -64,7 +69,7 @@ def test_stage_matches_the_reference_driver(path):
     comp = _compressor(m, w)
     ids = torch.tensor([m["prompt_ids"]], device="cuda")
     seq, selected, bounds = tdc_video_stage(comp, frames, torch.from_numpy(dino).cuda(), input_ids=ids,
-                                            max_visual_len=m["max_visual_len"], return_segments=True)
+                                            max_visual_len=m["max_visual_len"], return_segments=True, **audio_kw)
     torch.cuda.synchronize()
     # segmentation: the same boundaries as the reference's adapt_segment chose
     assert selected.tolist() == list(range(n))
