@@ -79,6 +79,7 @@ DRIVER_CASES = {
     "avgpool_text_33f": (33, 8, "Avg_pool", True, True, 100000, None),
     "learned_notext_budget_30f": (30, 8, "learned", False, True, 2600, None),
     "avgpool_text_audio_sparse_27f": (27, 8, "Avg_pool", True, True, 100000, "sparse"),
+    "avgpool_notext_nostatic_230f": (230, 8, "Avg_pool", False, False, 100000, None),   # > 224 frames: subsample
 }
 
 
@@ -147,10 +148,13 @@ def make_driver_goldens(only=None):
             windows, flags, seconds, proj = driver_audio(60 + n, n, audio)
             w.update(proj)
             akw = dict(audio_windows=windows, video_indices=torch.tensor(flags, dtype=torch.int16), audio_seconds=seconds)
+        elif n > 224:   # the > 224-frame branch indexes video_indices[i] (cambrian_arch.py:918-921): it must be a tensor
+            akw = dict(video_indices=torch.ones(n, dtype=torch.int16))
         ref = harness.run_reference_driver(w, DRIVER_GEOM, n, d_llm=DRIVER_D, context_token_num=K, query_type=qt,
                                            text_input=text, add_static=static, tokenizer_model_max_length=max_len,
                                            prompt_ids=[[3, 9, 4, 1]], siglip_table=sig, dino_table=dino, **akw)
-        assert torch.allclose(ref["frames"], driver_frames(w, sig, dino), atol=1e-6)
+        kept = list(range(n)) if n <= 224 else [int(n / 224.0 * i) for i in range(224)]   # cambrian_arch.py:908-916
+        assert torch.allclose(ref["frames"], driver_frames(w, sig, dino)[kept], atol=1e-6)
         meta = dict(n_frames=n, num_query=K, query_type=qt, text=text, add_static=static,
                     tokenizer_model_max_length=max_len, max_visual_len=max_len - 16 - 3, prompt_ids=[3, 9, 4, 1],
                     weight_seed=40 + n, table_seed=50 + n, audio=audio, audio_seed=60 + n,

@@ -63,8 +63,16 @@ def tdc_video_stage(compressor: TDCCompressor, visual_emb_frame: torch.Tensor, d
     sizes = segment_sizes(boundaries, n)
     audio_frames = None
     if audio_windows is not None:
-        # sample_indices are 0/1 flags per SECOND of the clip, not per kept frame: used as they are (:1563-1581)
-        audio_frames = pool_audio_per_frame(audio_windows, sample_indices, n)
+        # sample_indices: 0/1 per SECOND of the clip, 1 = a frame was sampled there (default: 1 fps, every second).
+        # When frames were dropped by the > 224 subsample, only the kept frames' seconds stay flagged (:917-925).
+        n_in = dino_features.shape[0]
+        si = torch.ones(n_in, dtype=torch.int16) if sample_indices is None else torch.as_tensor(sample_indices).cpu()
+        if len(selected) != n_in:
+            pos = torch.where(si == 1)[0]
+            kept = torch.zeros_like(si)
+            kept[pos[selected]] = 1
+            si = kept
+        audio_frames = pool_audio_per_frame(audio_windows, si, n)
     seq = compressor.compress_video(visual_emb_frame, sizes, input_ids=input_ids, audio_frames=audio_frames,
                                     max_visual_len=max_visual_len, shard=shard)
     if return_segments:

@@ -21,13 +21,15 @@ def test_driver_oracle_matches_reference_golden(path):
     m = json.loads(str(z["meta"]))
     w = driver_weights(m["weight_seed"], m["num_query"])
     sig, dino = driver_tables(m["table_seed"], m["n_frames"])
-    frames = driver_frames(w, sig, dino)
-    sizes = driver_oracle.segment_sizes_from_boundaries(z["segment_frame_indices"], m["n_frames"])
+    n = m["n_frames"]
+    kept = list(range(n)) if n <= 224 else [int(n / 224.0 * i) for i in range(224)]   # cambrian_arch.py:908-916
+    frames = driver_frames(w, sig, dino)[kept]
+    sizes = driver_oracle.segment_sizes_from_boundaries(z["segment_frame_indices"], len(kept))
     audio_frames = None
     if m.get("audio"):
         windows, flags, _, proj = driver_audio(m["audio_seed"], m["n_frames"], m["audio"])
         w.update(proj)
-        audio_frames = driver_oracle.audio_frames_from_beats(windows, flags, m["n_frames"])
+        audio_frames = driver_oracle.audio_frames_from_beats(windows, flags, len(kept))
     got = driver_oracle.compress_video(w, DRIVER_GEOM, frames, sizes, context_token_num=m["num_query"],
                                        query_type=m["query_type"], add_text=m["text"], keep_static=m["add_static"],
                                        input_ids=torch.tensor([m["prompt_ids"]]), max_visual_len=m["max_visual_len"],
@@ -37,4 +39,4 @@ def test_driver_oracle_matches_reference_golden(path):
 
 
 def test_driver_goldens_exist():
-    assert len(GOLDEN) >= 3
+    assert len(GOLDEN) >= 4

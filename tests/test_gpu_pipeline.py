@@ -72,7 +72,8 @@ def test_stage_matches_the_reference_driver(path):
                                             max_visual_len=m["max_visual_len"], return_segments=True, **audio_kw)
     torch.cuda.synchronize()
     # segmentation: the same boundaries as the reference's adapt_segment chose
-    assert selected.tolist() == list(range(n))
+    kept = list(range(n)) if n <= 224 else [int(n / 224.0 * i) for i in range(224)]   # cambrian_arch.py:908-916
+    assert selected.tolist() == kept
     assert bounds.cpu().tolist() == z["segment_frame_indices"].tolist()
     ref = torch.from_numpy(z["visual_tokens"])
     assert tuple(seq.shape) == tuple(ref.shape)
