@@ -145,18 +145,8 @@ class TDCCompressor(nn.Module):
         q = linear(pooled, self.query_proj.weight, self.query_proj.bias, out_dtype=torch.float32)
         return q, False
 
-    @torch.no_grad()
-    def compress_video(self, visual_emb_frame: torch.Tensor, segment_sizes: Sequence[int],
-                       input_ids: Optional[torch.Tensor] = None, audio_frames: Optional[torch.Tensor] = None,
-                       max_visual_len: Optional[int] = None, return_parts: bool = False, group=None,
-                       shard: bool = False):
-        """visual_emb_frame [n_frames, Lv, d] (one video), segment_sizes (frames per DINO segment),
-        input_ids [1, T] BERT ids of the prompt (used iff text_input), audio_frames [n_frames, La, 768]
-        per-frame BEATs tokens (iff the video has audio).  Returns the token sequence
-        `new_visual_emb_frames[:max_visual_len]` of cambrian_arch.py:1694-1709.
-
-        shard=True (inside an initialised torch.distributed job): every rank holds the same inputs,
-        compresses a contiguous range of chunks and one all-gather assembles all rows on every rank."""
+    # ---- one video = prepare (KV tokens, queries) -> Q-Former rows -> assemble --------------------
+    def _prepare(self, visual_emb_frame, segment_sizes, input_ids, audio_frames):
         if self.training:
             raise RuntimeError("TDCCompressor is inference-only (eval mode)")
         if not visual_emb_frame.is_cuda:
@@ -165,9 +155,8 @@ class TDCCompressor(nn.Module):
         if sum(int(s) for s in segment_sizes) != n_frames:
             raise ValueError("segment_sizes must sum to the number of frames")
         dev, dtype = visual_emb_frame.device, visual_emb_frame.dtype
-        K = self.context_token_num
         plan = plan_chunks(segment_sizes, self.add_static)
-        C_, R = plan.num_chunks, plan.num_rows
+        R = plan.num_rows
         static_idx = torch.from_numpy(plan.static_frames).to(dev)
         row_idx = torch.from_numpy(plan.row_frames).to(dev)
 
@@ -193,14 +182,59 @@ class TDCCompressor(nn.Module):
         static_visual = static_tok[:, :Lv] if La else static_tok
 
         # --- queries (one set per chunk) and prompt ids (one set per video)
-        comp = None
+        q_sets = query_set = ids = None
         if R > 0:
             q_sets, shared = self.build_queries(static_visual.contiguous())
             query_set = torch.zeros(R, dtype=torch.int32) if shared else torch.from_numpy(plan.row_chunk.astype(np.int32))
-            ids = text_set = None
             if self.text_input and input_ids is not None and input_ids.numel() > 0:
                 ids = input_ids.reshape(1, -1)
-                text_set = torch.zeros(R, dtype=torch.int32)
+        return dict(plan=plan, enc=enc, static_tok=static_tok, q_sets=q_sets, query_set=query_set, ids=ids, L=L, d=d,
+                    dev=dev, dtype=dtype)
+
+    def _assemble(self, prep, comp, max_visual_len):
+        """[static, sep, (K compressed, sep) x rows] per chunk (:1668-1692), then the budget truncation (:1694-1709)."""
+        plan, L, d, dev, dtype = prep["plan"], prep["L"], prep["d"], prep["dev"], prep["dtype"]
+        K = self.context_token_num
+        chunk_off, chunk_tok, row_off = output_layout(plan, L, K, self.add_static, add_sep=True)
+        total = int(chunk_tok.sum())
+        out = torch.empty((total, d), dtype=dtype, device=dev)
+        seg = self.frame_seg.detach().to(dtype)
+        sep_pos = []
+        if self.add_static and plan.num_chunks > 0:
+            idx = (chunk_off[:, None] + np.arange(L)[None, :]).reshape(-1)
+            out.index_copy_(0, torch.from_numpy(idx).to(dev), prep["static_tok"].reshape(-1, d))
+            sep_pos.append(chunk_off + L)
+        if plan.num_rows > 0:
+            idx = (row_off[:, None] + np.arange(K)[None, :]).reshape(-1)
+            out.index_copy_(0, torch.from_numpy(idx).to(dev), comp.reshape(-1, d))
+            sep_pos.append(row_off + K)
+        if sep_pos:
+            sp = torch.from_numpy(np.concatenate(sep_pos)).to(dev)
+            out.index_copy_(0, sp, seg[None, :].expand(sp.numel(), d).contiguous())
+        keep = truncation_keep_index(chunk_off, chunk_tok, max_visual_len)
+        if keep is not None:
+            out = out.index_select(0, torch.from_numpy(keep).to(dev))
+        return out
+
+    @torch.no_grad()
+    def compress_video(self, visual_emb_frame: torch.Tensor, segment_sizes: Sequence[int],
+                       input_ids: Optional[torch.Tensor] = None, audio_frames: Optional[torch.Tensor] = None,
+                       max_visual_len: Optional[int] = None, return_parts: bool = False, group=None,
+                       shard: bool = False):
+        """visual_emb_frame [n_frames, Lv, d] (one video), segment_sizes (frames per DINO segment),
+        input_ids [1, T] BERT ids of the prompt (used iff text_input), audio_frames [n_frames, La, 768]
+        per-frame BEATs tokens (iff the video has audio).  Returns the token sequence
+        `new_visual_emb_frames[:max_visual_len]` of cambrian_arch.py:1694-1709.
+
+        shard=True (inside an initialised torch.distributed job): every rank holds the same inputs,
+        compresses a contiguous range of chunks and one all-gather assembles all rows on every rank."""
+        prep = self._prepare(visual_emb_frame, segment_sizes, input_ids, audio_frames)
+        plan, enc, dtype = prep["plan"], prep["enc"], prep["dtype"]
+        R = plan.num_rows
+        comp = None
+        if R > 0:
+            q_sets, query_set, ids = prep["q_sets"], prep["query_set"], prep["ids"]
+            text_set = None if ids is None else torch.zeros(R, dtype=torch.int32)
             sharded = shard and torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size(group) > 1
             if not sharded:
@@ -215,28 +249,50 @@ class TDCCompressor(nn.Module):
                                                 text_set=None if text_set is None else text_set[r_lo:r_hi],
                                                 out_dtype=dtype)
                 comp = tdist.all_gather_rows(local, [hi - lo for lo, hi in row_ranges], group)
-
-        # --- assemble [static, sep, (K compressed, sep) x rows] per chunk (:1668-1692)
-        Ls = L
-        chunk_off, chunk_tok, row_off = output_layout(plan, Ls, K, self.add_static, add_sep=True)
-        total = int(chunk_tok.sum())
-        out = torch.empty((total, d), dtype=dtype, device=dev)
-        seg = self.frame_seg.detach().to(dtype)
-        sep_pos = []
-        if self.add_static and C_ > 0:
-            idx = (chunk_off[:, None] + np.arange(Ls)[None, :]).reshape(-1)
-            out.index_copy_(0, torch.from_numpy(idx).to(dev), static_tok.reshape(-1, d))
-            sep_pos.append(chunk_off + Ls)
-        if R > 0:
-            idx = (row_off[:, None] + np.arange(K)[None, :]).reshape(-1)
-            out.index_copy_(0, torch.from_numpy(idx).to(dev), comp.reshape(-1, d))
-            sep_pos.append(row_off + K)
-        if sep_pos:
-            sp = torch.from_numpy(np.concatenate(sep_pos)).to(dev)
-            out.index_copy_(0, sp, seg[None, :].expand(sp.numel(), d).contiguous())
-        keep = truncation_keep_index(chunk_off, chunk_tok, max_visual_len)
-        if keep is not None:
-            out = out.index_select(0, torch.from_numpy(keep).to(dev))
+        out = self._assemble(prep, comp, max_visual_len)
         if return_parts:
             return out, comp, plan
         return out
+
+    @torch.no_grad()
+    def compress_videos(self, videos: Sequence[dict]) -> List[torch.Tensor]:
+        """Several videos at once (the eval-style workload: many concurrent clips): the rows of all videos that
+        share a KV length and a prompt length go through ONE tdc_compress call, instead of one call per video (and
+        one per <= 7 rows in the reference).  Every item is a dict with the arguments of `compress_video`:
+        `visual_emb_frame`, `segment_sizes`, optional `input_ids`, `audio_frames`, `max_visual_len`.
+        Returns one token sequence per video, equal bit for bit to calling `compress_video` per video."""
+        preps = [self._prepare(v["visual_emb_frame"], v["segment_sizes"], v.get("input_ids"), v.get("audio_frames"))
+                 for v in videos]
+        comps: List[Optional[torch.Tensor]] = [None] * len(videos)
+        groups = {}
+        for i, p in enumerate(preps):
+            if p["plan"].num_rows > 0:
+                T = 0 if p["ids"] is None else int(p["ids"].shape[1])
+                groups.setdefault((p["L"], T, p["dtype"], p["q_sets"].shape[0] == 1 and self.query_type == "learned"),
+                                  []).append(i)
+        for (L, T, dtype, shared), members in groups.items():
+            encs, qsets, qmaps, tmaps, idss = [], [], [], [], []
+            set_base = 0
+            for g, i in enumerate(members):
+                p = preps[i]
+                R = p["plan"].num_rows
+                encs.append(p["enc"])
+                if shared:                       # learned queries: one set serves every row of every video
+                    qmaps.append(torch.zeros(R, dtype=torch.int32))
+                else:
+                    qsets.append(p["q_sets"])
+                    qmaps.append(p["query_set"] + set_base)
+                    set_base += p["q_sets"].shape[0]
+                if T > 0:
+                    idss.append(p["ids"])
+                    tmaps.append(torch.full((R,), g, dtype=torch.int32))
+            q_all = preps[members[0]]["q_sets"] if shared else torch.cat(qsets, dim=0)
+            out = self._engine().compress(q_all, torch.cat(encs, dim=0) if len(encs) > 1 else encs[0],
+                                          torch.cat(idss, dim=0) if T > 0 else None, query_set=torch.cat(qmaps),
+                                          text_set=torch.cat(tmaps) if T > 0 else None, out_dtype=dtype)
+            r0 = 0
+            for i in members:
+                R = preps[i]["plan"].num_rows
+                comps[i] = out[r0:r0 + R]
+                r0 += R
+        return [self._assemble(p, c, v.get("max_visual_len")) for p, c, v in zip(preps, comps, videos)]

@@ -122,6 +122,44 @@ def test_compressor_matches_reference_loop(query_type, text, audio, keep_static)
         _metrics_ok(seq, ref, f"compressor {query_type} text={text} audio={audio} budget={budget}")
 
 
+@pytest.mark.parametrize("query_type", ["Avg_pool", "learned"])
+def test_compress_videos_batches_many_videos_bit_exactly(query_type):
+    """The eval-style workload (many concurrent clips, BASELINE config 5): rows of all videos with the same KV and
+    prompt length go through one tdc_compress call; rows are independent, so every video's sequence must equal
+    the per-video call bit for bit.  Mixed: audio / silent videos, two prompt lengths, a one-frame video (no rows)."""
+    from tdc_video_b200.compressor import TDCCompressor
+    cfg = _small_cfg()
+    d = 64
+    comp = TDCCompressor(d, context_token_num=16, query_type=query_type, text_input=True, add_static=True,
+                         audio_input=True, qformer_config=cfg)
+    _randomize(comp, 4)
+    comp = comp.cuda().eval()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    spec = [([3, 1, 9, 2], 5, True, None), ([4, 4], 5, False, 120), ([1], 5, False, None), ([2, 11], 3, True, None),
+            ([6, 1, 1], 5, True, 200), ([5], 3, False, None)]
+    videos = []
+    for sizes, T, audio, budget in spec:
+        n = sum(sizes)
+        videos.append(dict(visual_emb_frame=torch.randn(n, 20, d, device="cuda", generator=g), segment_sizes=sizes,
+                           input_ids=torch.randint(0, 40, (1, T), device="cuda", generator=g),
+                           audio_frames=torch.randn(n, 6, 768, device="cuda", generator=g) if audio else None,
+                           max_visual_len=budget))
+    eng = comp._engine()
+    calls0 = eng.launch_count()
+    batched = comp.compress_videos(videos)
+    launches_batched = eng.launch_count() - calls0
+    calls0 = eng.launch_count()
+    single = [comp.compress_video(v["visual_emb_frame"], v["segment_sizes"], input_ids=v["input_ids"],
+                                  audio_frames=v["audio_frames"], max_visual_len=v["max_visual_len"]) for v in videos]
+    launches_single = eng.launch_count() - calls0
+    torch.cuda.synchronize()
+    assert len(batched) == len(videos)
+    for i, (a, b) in enumerate(zip(batched, single)):
+        assert a.shape == b.shape and torch.equal(a, b), i
+    # 4 groups (audio x prompt length) instead of 5 calls with rows
+    assert launches_batched < launches_single
+
+
 def test_gelu_mlp_projector_and_linear():
     """mm_projector Linear-GELU(erf)-Linear (cambrian_arch.py:65-69) on the tcgen05 GEMM."""
     from tdc_video_b200 import linear
