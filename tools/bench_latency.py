@@ -1,0 +1,65 @@
+"""Latency of the TDC stage for ONE reference-sized video (what main.py / eval_*.py do per question):
+224 frames (the reference's cap, cambrian_arch.py:908), 24 adaptive boundaries, Qwen2-7B widths, 156 visual + 50
+audio tokens per frame, K = 16, a 32-token prompt -> `pipeline.tdc_video_stage` (adapt_segment, audio pooling,
+chunked Q-Former compression, assembly).  Wall clock around the call incl. all host logic, after warm-up.
+Prints one JSON line; run on a B200: python tools/bench_latency.py"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tdc_video_b200.compressor import TDCCompressor  # noqa: E402
+from tdc_video_b200.pipeline import tdc_video_stage  # noqa: E402
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    n, d, T = 224, 3584, 32
+    comp = TDCCompressor(d, context_token_num=16, query_type="Avg_pool", text_input=True, add_static=True,
+                         audio_input=True).to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(5)
+    frames = torch.randn(n, 156, d, device=dev, generator=g).to(torch.bfloat16)
+    # DINO features: slow drift + a jump every ~9 frames so that the 24 boundaries are well defined
+    drift = torch.cumsum(torch.randn(n, 1, 1536, device=dev, generator=g) * 0.05, 0)
+    dino = (torch.randn(1, 576, 1536, device=dev, generator=g) + drift)
+    dino[::9] += torch.randn(len(range(0, n, 9)), 1, 1536, device=dev, generator=g)
+    dino = dino.to(torch.bfloat16)
+    windows = [torch.randn(1, 500 if w < 22 else 200, 768, device=dev, generator=g).to(torch.bfloat16) for w in range(23)]
+    flags = [1] * n
+    ids = torch.randint(1000, 30000, (1, T), device=dev, generator=g)
+    kw = dict(input_ids=ids, audio_windows=windows, sample_indices=flags, max_visual_len=32000)
+
+    def run():
+        return tdc_video_stage(comp, frames, dino, **kw)
+
+    for _ in range(3):
+        out = run()
+    torch.cuda.synchronize()
+    walls, devs = [], []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record()
+        out = run()
+        e1.record()
+        torch.cuda.synchronize()
+        walls.append((time.perf_counter() - t0) * 1e3)
+        devs.append(e0.elapsed_time(e1))
+    _, comp_rows, plan = comp.compress_video(frames, [9] * 24 + [8], input_ids=ids, return_parts=True)
+    print(json.dumps({
+        "metric": "TDC stage latency, one 224-frame video (Qwen2-7B widths, L=206, K=16, T=32, audio)",
+        "wall_ms_median": float(np.median(walls)), "wall_ms_min": float(min(walls)),
+        "device_ms_median": float(np.median(devs)), "output_tokens": int(out.shape[0]),
+        "rows": int(plan.num_rows), "chunks": int(plan.num_chunks),
+        "reference_launch_pattern": f"{plan.num_chunks} Q-Former calls of <= 7 rows (cambrian_arch.py:1603-1692)",
+        "finite": bool(torch.isfinite(out.float()).all())}))
+
+
+if __name__ == "__main__":
+    main()
