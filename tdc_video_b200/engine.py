@@ -38,7 +38,7 @@ class QFormerEngine:
 
     def __init__(self, *, hidden=768, heads=12, intermediate=3072, layers=12, cross_freq=2, d_enc=3584, d_out=0,
                  vocab=0, max_pos=512, ln_eps=1e-12, device=None, gemm_cta_group=0,
-                 max_workspace_bytes: int = 24 << 30):
+                 max_workspace_bytes: int = 8 << 30):
         if not torch.cuda.is_available():
             raise RuntimeError("tdc_video_b200 needs a CUDA (sm_100a) device: there is no CPU fallback")
         self.lib = _lib.load_library()
