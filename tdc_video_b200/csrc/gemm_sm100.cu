@@ -482,11 +482,12 @@ int launch_variant(const GemmProblem& p, cudaStream_t stream, const char** err) 
   auto pick = [](char ch, unsigned long long dflt) -> unsigned long long {
     return ch == 'n' ? kL2EvictNormal : ch == 'f' ? kL2EvictFirst : ch == 'l' ? kL2EvictLast : dflt;
   };
+  static const int debug_skip_epilogue = [] { const char* e = getenv("TDC_GEMM_DEBUG"); return (e && atoi(e) == 1) ? 1 : 0; }();
   const bool he = hints_env != nullptr && strlen(hints_env) == 3;
   EpilogueArgs e{p.bias, p.mode, p.slab_cols > 0 ? p.slab_cols : p.n,
                  pick(he ? hints_env[0] : 0, kL2EvictNormal), pick(he ? hints_env[1] : 0, kL2EvictLast),
                  pick(he ? hints_env[2] : 0, kL2EvictNormal),
-                 (getenv("TDC_GEMM_DEBUG") != nullptr && atoi(getenv("TDC_GEMM_DEBUG")) == 1) ? 1 : 0};
+                 debug_skip_epilogue};
   // N-tile group whose W slice fits a quarter of the 126 MB L2 (the L2 is two ~63 MB halves and
   // read-shared lines end up in both), balanced over the groups.
   const int num_n_tiles = (p.n + BLOCK_N - 1) / BLOCK_N;
