@@ -164,7 +164,7 @@ class QFormerEngine:
     def compress_host(self, query_embeds: torch.Tensor, enc_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
                       *, query_set: Optional[torch.Tensor] = None, input_ids: Optional[torch.Tensor] = None,
                       text_set: Optional[torch.Tensor] = None, rows_per_batch: int = 1024,
-                      out_device: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      out_device: Optional[torch.Tensor] = None, taper_tail: bool = True) -> torch.Tensor:
         """`compress` for inputs that live in (pinned) HOST memory: enc_host [rows, L, d_enc] is streamed
         to the GPU in row batches on a copy stream while the previous batch computes, and each batch's
         [n, K, d_out] result is copied back to `out_host` on a third stream.  Stream-ordered: the
@@ -189,8 +189,20 @@ class QFormerEngine:
         ts_dev = None if text_set is None else text_set.to(dev, torch.int32)
         ids_dev = None if input_ids is None else input_ids.to(dev)
         self._h2d_stream.wait_stream(cur)
-        for i, r0 in enumerate(range(0, rows, rb)):
-            r1, b = min(r0 + rb, rows), i % 2
+        # The stream is transfer-bound (PCIe), so what the caller waits for after the last byte has arrived is the
+        # last batch's compute + read-back: taper the tail (rb, ..., rb/2, rb/4, ..., 64-128 rows) to keep that short.
+        bounds, r0 = [], 0
+        while rows - r0 > rb:
+            bounds.append((r0, r0 + rb))
+            r0 += rb
+        while rows - r0 > 128 and taper_tail:
+            step = (rows - r0) // 2
+            bounds.append((r0, r0 + step))
+            r0 += step
+        if r0 < rows:
+            bounds.append((r0, rows))
+        for i, (r0, r1) in enumerate(bounds):
+            b = i % 2
             with torch.cuda.stream(self._h2d_stream):
                 if i >= 2:
                     self._h2d_stream.wait_event(compute_done[b])   # staging buffer free again
