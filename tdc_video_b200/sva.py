@@ -62,17 +62,19 @@ def window_mask_bits(image_sizes: Sequence[Tuple[int, int]], grids: Sequence[int
 
 
 def _layernorm(x: torch.Tensor, ln: nn.LayerNorm, *, resid: Optional[torch.Tensor] = None, resid_period: int = 0,
-               want_f32: bool = False):
-    """LayerNorm(x [+ resid]) through tdc_layernorm: x fp32 [rows, width] -> bf16 (and fp32 if asked)."""
+               want_f32: bool = False, want_bf16: bool = True):
+    """LayerNorm(x [+ resid]) through tdc_layernorm: x fp32 [rows, width] -> bf16 and/or fp32 copies."""
     lib = _lib.load_library()
     rows, width = x.shape
-    y16 = torch.empty((rows, width), dtype=torch.bfloat16, device=x.device)
+    y16 = torch.empty((rows, width), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
     y32 = torch.empty((rows, width), dtype=torch.float32, device=x.device) if want_f32 else None
     with torch.cuda.device(x.device):
         rc = lib.tdc_layernorm(_ptr(x), _ptr(resid), resid_period, _ptr(ln.weight), _ptr(ln.bias), float(ln.eps),
                                _ptr(y32), _ptr(y16), rows, width, _stream(x.device))
     _lib.check(rc, None, "tdc_layernorm")
-    return (y16, y32) if want_f32 else y16
+    if want_f32 and want_bf16:
+        return y16, y32
+    return y32 if want_f32 else y16
 
 
 class _Params(nn.Module):
@@ -182,15 +184,18 @@ class SVAConnector(nn.Module):
         latents, feat0 = [], None
         for t, x in enumerate(tower_feats):
             seq = getattr(self, f"mm_projector_aux_{t}")
-            h = linear(x.to(torch.bfloat16), self._w(seq[0]), seq[0].bias, gelu=True)
-            y = linear(h, self._w(seq[2]), seq[2].bias, out_dtype=torch.float32).reshape(-1, H)
-            _, f32 = _layernorm(y, seq[3], want_f32=True)
-            f32 = f32.view(bs, grids[t] * grids[t], H)
-            if t == 0:
-                feat0 = f32
             r = self.window_sides[t]
-            # tokens under every query, window-major (cambrian_arch.py:624-645): pure data movement
-            latents.append(f32.view(bs, Q, r, Q, r, H).permute(0, 1, 3, 2, 4, 5).reshape(R * r * r, H).contiguous())
+            # tokens under every query, window-major (cambrian_arch.py:624-645).  The projector acts on each token
+            # separately and the context is a mean over tokens, so the rearrangement is applied to the (narrow,
+            # bf16) tower features instead of the projector's fp32 output: pure data movement, fused with the cast.
+            xw = torch.empty((bs, Q, Q, r, r, x.shape[-1]), dtype=torch.bfloat16, device=dev)
+            xw.copy_(x.reshape(bs, Q, r, Q, r, -1).permute(0, 1, 3, 2, 4, 5))
+            h = linear(xw.view(R * r * r, -1), self._w(seq[0]), seq[0].bias, gelu=True)
+            y = linear(h, self._w(seq[2]), seq[2].bias, out_dtype=torch.float32)
+            f32 = _layernorm(y, seq[3], want_f32=True, want_bf16=False)              # [R * r * r, H] fp32
+            if t == 0:
+                feat0 = f32.view(bs, grids[t] * grids[t], H)
+            latents.append(f32)
         context = avg_pool_tokens(feat0, 1).reshape(bs, H)                       # global context = token mean (:1009)
         q32 = self.vision_query.detach()[0].float().view(1, H).expand(R, H).contiguous()
         q16 = q32.to(torch.bfloat16)
