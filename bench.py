@@ -1,14 +1,15 @@
 #!/usr/bin/env python
 """bench.py — TDC compression throughput (video-seconds/s) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload hour_qwen7b|cfg2_llama3b]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload hour_qwen7b|cfg2_llama3b|...] [--num-text T]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the reference algorithm on the host CPU cores
 
 One "step" = one pass of the hot path over one synthetic video per GPU: for every dynamic
 frame (row) the Q-Former (12 layers, cross-attention to the frame's L KV tokens) + vision_proj
-+ L2-normalise, i.e. tdc/cambrian_arch.py:1603-1692 for all chunks at once, then (N > 1) an
-NCCL all-gather of the compressed tokens so that every rank holds the ordered sequence.
++ L2-normalise, i.e. tdc/cambrian_arch.py:1603-1692 for all chunks at once, then (N > 1) the
+all-gather of the compressed tokens so that every rank holds the ordered sequence (fused into the
+final kernel through NVSwitch multicast stores; `--no-multicast` = NCCL all-gather).
 
  * `value`  : whole-job video-seconds/s, inputs resident in HBM, CUDA-event timed, max over ranks
  * `e2e`    : the same through `QFormerEngine.compress_host` with the KV tokens in pinned HOST
