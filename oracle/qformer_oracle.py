@@ -22,7 +22,7 @@ tests for this path, so outputs of the reference run here are th
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 import torch.nn.functional as F

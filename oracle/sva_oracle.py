@@ -19,8 +19,7 @@ PINNING: tests/test_sva_pinning.py compares every function with the reference's 
 """
 from __future__ import annotations
 
-import math
-from typing import Dict, List, Sequence, Tuple
+from typing import Sequence, Tuple
 
 import torch
 import torch.nn.functional as F

@@ -7,7 +7,6 @@ raised.  Nothing here imports the CPU oracle.
 from __future__ import annotations
 
 import ctypes as C
-import os
 from pathlib import Path
 from typing import Optional
 

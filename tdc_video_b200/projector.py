@@ -10,8 +10,6 @@ tcgen05 GEMMs with bias + exact-erf GELU fused into the first epilogue.  CUDA on
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import torch
 from torch import nn
 

@@ -9,7 +9,6 @@ over the flattened DINO features (:832-842) and `sort(argsort(sims)[:max_num_seg
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import List, Tuple
 
 import torch

@@ -16,7 +16,7 @@ per-row key mask (`tdc_attention`; one query against r0^2 + r1^2 keys, two-segme
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 import torch

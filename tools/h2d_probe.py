@@ -4,7 +4,6 @@ PROBE_BIND=1 pins every rank to its GPU's NUMA node first (what bench.py does)."
 import json
 import os
 import sys
-import time
 
 import torch
 import torch.distributed as dist

@@ -1,8 +1,6 @@
 """torchrun probe: does torch symmetric memory (peer pointers / NVSwitch multicast) work on this box,
 and how fast are NCCL all-gather vs direct peer copies for the bench payload?"""
 import os
-import sys
-import time
 
 import torch
 import torch.distributed as dist
