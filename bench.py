@@ -398,8 +398,14 @@ def main():
     prof = eng.profile()
     eng.set_profiling(False)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    # every rank's own device time and kernel-time sum (the step ends at a barrier, so `value` follows the slowest GPU)
+    mine = torch.tensor([ms / args.steps, sum(v["ms"] for v in prof.values()) / args.steps], dtype=torch.float64, device=dev)
+    per_rank = [mine.clone() for _ in range(world)]
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_gather(per_rank, mine)
+    per_rank = {"ms_per_step": [round(float(x[0]), 2) for x in per_rank],
+                "kernel_ms_per_step": [round(float(x[1]), 2) for x in per_rank]}
     ms_step = float(t.item()) / args.steps
     value = world * S / (ms_step * 1e-3)
 
@@ -468,6 +474,7 @@ def main():
         "path": {"algorithmic_tflops": path_tflops, "frac_of_sustained_peak": path_tflops / peaks["tflops_sustained"],
                  "gflop_per_row": f_row / 1e9,
                  "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}},
+        "ranks": per_rank,
     }
     if not args.no_cpu_baseline:
         passes = args.cpu_passes or 10
