@@ -70,3 +70,19 @@ def test_reference_token_accounting_example():
     plan = plan_chunks(sizes)
     _, tok, _ = output_layout(plan, 156, 16)
     assert plan.num_chunks == 25 and plan.num_rows == 35 and int(tok.sum()) == 25 * 157 + 35 * 17 == 4520
+
+
+def test_append_newline_tokens_and_stage_guards():
+    """pipeline.py host-side pieces: the newline column layout (cambrian_arch.py:1269-1281) is pure data movement
+    and the composed stage refuses CPU tensors (no fallback)."""
+    import torch
+    from tdc_video_b200.pipeline import append_newline_tokens, tdc_video_stage
+    x = torch.arange(2 * 16 * 3, dtype=torch.float32).view(2, 16, 3)
+    nl = torch.tensor([-1.0, -2.0, -3.0])
+    y = append_newline_tokens(x, nl)
+    ref = torch.cat([x.view(2, 4, 4, 3), nl.view(1, 1, 1, 3).expand(2, 4, 1, 3)], dim=2).flatten(1, 2)
+    assert y.shape == (2, 20, 3) and torch.equal(y, ref)
+    with pytest.raises(ValueError):
+        append_newline_tokens(x[:, :15], nl)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tdc_video_stage(None, torch.zeros(3, 20, 8), torch.zeros(3, 4, 8))
