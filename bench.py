@@ -208,6 +208,24 @@ def cpu_baseline(geom, sd, w, sample_rows, seed, passes=1):
     return rows_per_s / (w["frames_per_segment"] - 1), dt, cores
 
 
+def cpu_baseline_reference_batching(geom, sd, w, sample_rows, seed):
+    """The same CPU port called the way the reference's chunk loop calls the Q-Former: <= 7 rows per call
+    (tdc/cambrian_arch.py:1603-1692), one pass over the sample."""
+    from oracle import qformer_oracle as oracle
+    from tdc_video_b200.synth import make_inputs
+    T = w.get("num_text", 0)
+    inp = make_inputs(geom, seed, sample_rows, w["kv_tokens"], w["num_query"], T, audio_tokens=w["audio_tokens"])
+    sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
+    ids = None if T == 0 else np.repeat(inp["input_ids"][:1], sample_rows, axis=0)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        for r0 in range(0, sample_rows, 7):
+            sl = slice(r0, min(r0 + 7, sample_rows))
+            oracle.compress(sd_t, geom, inp["query_embeds"][sl], inp["enc"][sl], None if ids is None else ids[sl])
+        dt = time.perf_counter() - t0
+    return sample_rows / dt / (w["frames_per_segment"] - 1)
+
+
 def run_reference_arm(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -482,6 +500,10 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "video-s/s", "cores": cores, "kind": "port",
                                 "sample": f"{passes} x {args.cpu_sample_rows} rows of the same workload in {dt:.1f} s "
                                           f"(oracle port of the reference, fp32 torch, {args.cpu_sample_rows}-row batches)"}
+        if w["projector"] == "vision_proj":
+            line["cpu_baseline"]["reference_batching"] = {
+                "rows_per_call": 7, "unit": "video-s/s",
+                "value": cpu_baseline_reference_batching(geom, sd, w, args.cpu_sample_rows, 99)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
