@@ -264,7 +264,7 @@ def main():
     ap.add_argument("--segments", type=int, default=0, help="override segments per GPU")
     ap.add_argument("--cpu-sample-rows", type=int, default=96, help="rows per CPU batch (cpu_baseline / reference arm)")
     ap.add_argument("--cpu-passes", type=int, default=0,
-                    help="passes over the CPU sample (default: 10 for cpu_baseline = about 10-20 s, 2 per reference-arm step)")
+                    help="passes over the CPU sample (default: 16 for cpu_baseline = about 10-20 s, 2 per reference-arm step)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-rows-per-batch", type=int, default=600,
                     help="row batch of the host-streaming leg (smaller = shorter pipeline fill/drain; the leg is PCIe-bound)")
@@ -495,7 +495,7 @@ def main():
         "ranks": per_rank,
     }
     if not args.no_cpu_baseline:
-        passes = args.cpu_passes or 10
+        passes = args.cpu_passes or 16
         v, dt, cores = cpu_baseline(geom, sd, w, args.cpu_sample_rows, 99, passes)
         line["cpu_baseline"] = {"value": v, "unit": "video-s/s", "cores": cores, "kind": "port",
                                 "sample": f"{passes} x {args.cpu_sample_rows} rows of the same workload in {dt:.1f} s "
