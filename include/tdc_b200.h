@@ -120,7 +120,9 @@ int tdc_proj_norm(tdc_handle* h, const void* hidden, int32_t hidden_dtype, int32
 /* Fused convenience entry: Q-Former + vision_proj + L2-normalise for all rows of a
  * video at once (the reference runs <= 7 rows per call from a Python loop,
  * cambrian_arch.py:1603-1692).  Arguments as tdc_qformer_forward; out is
- * [rows, K, d_out] (out_dtype). */
+ * [rows, K, d_out] (out_dtype).  Only the query tokens of the last layer are read
+ * (`[:, :K]`, :1665), so the text tokens' out-projection / feed-forward of that layer,
+ * which nothing consumes, are not computed. */
 int tdc_compress(tdc_handle* h, const void* query_embeds, int32_t query_dtype, const int32_t* query_set,
                  const int64_t* input_ids, const int32_t* text_set, const void* enc, int32_t enc_dtype,
                  const int32_t* kv_len, int32_t rows, int32_t kv_tokens, int32_t num_query, int32_t num_text,
