@@ -52,13 +52,46 @@ def main():
         walls.append((time.perf_counter() - t0) * 1e3)
         devs.append(e0.elapsed_time(e1))
     _, comp_rows, plan = comp.compress_video(frames, [9] * 24 + [8], input_ids=ids, return_parts=True)
+
+    # the Q-Former call alone (tdc_compress on the same rows): eager launches vs one CUDA-graph replay
+    prep = comp._prepare(frames, [9] * 24 + [8], ids, None)
+    eng = comp._engine()
+    R = prep["plan"].num_rows
+    args = (prep["q_sets"], prep["enc"], prep["ids"])
+    kws = dict(query_set=prep["query_set"].cuda(), text_set=torch.zeros(R, dtype=torch.int32, device=dev),
+               out_dtype=torch.bfloat16)
+
+    def timed(fn, n=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, (time.perf_counter() - t0) * 1e3 / n
+
+    eager_dev, eager_wall = timed(lambda: eng.compress(*args, **kws))
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            eng.compress(*args, **kws)
+    torch.cuda.current_stream().wait_stream(side)
+    graph_dev, graph_wall = timed(g.replay)
+    engine = {"rows": int(R), "eager_ms": eager_dev, "eager_wall_ms": eager_wall, "graph_ms": graph_dev,
+              "graph_wall_ms": graph_wall}
     print(json.dumps({
         "metric": "TDC stage latency, one 224-frame video (Qwen2-7B widths, L=206, K=16, T=32, audio)",
         "wall_ms_median": float(np.median(walls)), "wall_ms_min": float(min(walls)),
         "device_ms_median": float(np.median(devs)), "output_tokens": int(out.shape[0]),
         "rows": int(plan.num_rows), "chunks": int(plan.num_chunks),
         "reference_launch_pattern": f"{plan.num_chunks} Q-Former calls of <= 7 rows (cambrian_arch.py:1603-1692)",
-        "finite": bool(torch.isfinite(out.float()).all())}))
+        "tdc_compress_alone": engine, "finite": bool(torch.isfinite(out.float()).all())}))
 
 
 if __name__ == "__main__":
