@@ -278,6 +278,23 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand tile (the operand's M/N index is the contiguous one, e.g. a row-major [K, N] matrix used as B):
+// exactly what a 128B-swizzled TMA box of [k rows x 64 columns] delivers.  SBO = bytes between groups of 8 K rows
+// (1024 when the rows are dense), LBO = bytes between successive 64-element blocks along M/N.  Needs the
+// corresponding transpose bit of the instruction descriptor (bit 15 for A, bit 16 for B).
+// Verified on sm_100a by tools/umma_mnmajor_test.cu.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);       // [0,14)  start address >> 4
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;  // [16,30) leading byte offset
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;  // [32,46) stride byte offset
+  d |= static_cast<uint64_t>(1) << 46;                           // [46,48) descriptor version 1 (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                           // [61,64) layout = SWIZZLE_128B
+  return d;
+}
+constexpr uint32_t kIdescBMnMajor = 1u << 16;  // OR into make_idesc_bf16_f32(...) when B is MN-major
+constexpr uint32_t kIdescAMnMajor = 1u << 15;
+
 // kind::f16 instruction descriptor: A/B bf16 K-major, D fp32.
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int m, int n) {
   return (1u << 4)                             // [4,6)   D format = F32
