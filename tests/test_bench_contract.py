@@ -23,6 +23,18 @@ def test_flops_per_row_matches_baseline_table(L, d_enc, K, T, d_out, gflop):
     assert kv == 6 * 2 * 2 * L * d_enc * 768
 
 
+def test_variant_workloads_and_projector_flops():
+    """SURVEY 8.0 / 8d readings exist as --workload variants; the GELU-MLP projector flavour replaces
+    vision_proj's 2*K*768*d by 2*K*(768*d + d*d) in the per-row FLOPs (MLP projector formula of BASELINE.md)."""
+    lit, seg, ev = (bench.WORKLOADS[k] for k in ("literal_d1152_mlp", "segment_kv_d1152", "eval64x600"))
+    assert lit["d_enc"] == 1152 and lit["kv_tokens"] == 194 and lit["projector"] == "gelu_mlp"
+    assert seg["kv_tokens"] == 4 * 144 + 50 and seg["d_enc"] == 1152
+    assert ev["segments"] * 8 == 64 * 600
+    a, kv_a = bench.flops_per_row(194, 1152, 16, 0, 3584, "vision_proj")
+    b, kv_b = bench.flops_per_row(194, 1152, 16, 0, 3584, "gelu_mlp")
+    assert kv_a == kv_b and b - a == 2 * 16 * 3584 * 3584
+
+
 def test_default_workload_is_the_north_star_config():
     w = bench.WORKLOADS["hour_qwen7b"]
     assert w["segments"] == 3600 and w["d_enc"] == 3584 and w["d_out"] == 3584 and w["num_query"] == 16
