@@ -24,6 +24,8 @@
 #include "tdc_kernels.cuh"
 #include "tdc_ptx.cuh"
 
+#include <mutex>
+
 namespace tdc {
 
 namespace {
@@ -276,11 +278,18 @@ int attention_launch(const AttentionArgs& a, cudaStream_t stream, const char** e
     return TDC_EINVAL;
   }
   constexpr int kSmem = 4 * kStages * kSlotsPerStage * 16;  // 48 KB per 4-warp block -> 4 blocks / SM
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(tdc_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaFuncSetAttribute(tdc_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    attr_set = true;
+  {  // the opt-in is a per-device property: one flag per device ordinal
+    static std::mutex mu;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = (dev >= 0 && dev < 64) ? dev : 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!attr_set[dev]) {
+      cudaFuncSetAttribute(tdc_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+      cudaFuncSetAttribute(tdc_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+      attr_set[dev] = true;
+    }
   }
   if (a.q_seg2 > 0 || a.kv_seg2 > 0)
     tdc_attention_kernel<true><<<static_cast<unsigned>(blocks), 128, kSmem, stream>>>(a);

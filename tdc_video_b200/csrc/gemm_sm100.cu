@@ -28,8 +28,10 @@
 #include "tdc_ptx.cuh"
 #include "tdc_b200.h"
 
+#include <array>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 
 namespace tdc {
@@ -388,8 +390,30 @@ EncodeTiledFn get_encode_fn() {
 
 // 2-D row-major [rows, cols] (pitch ld elements, bf16 or fp32) -> boxes of box_rows x 128 bytes with
 // 128B swizzle (64 bf16 / 32 fp32 columns per box row).
-bool make_tensor_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows,
-                     bool f32 = false) {
+// cuTensorMapEncodeTiled costs ~1 us on the host and a forward pass issues ~190 of them per row batch with
+// a handful of distinct (pointer, shape) combinations (the workspace is reused call after call), so encoded
+// descriptors are memoised by their full argument list.  A descriptor is a pure function of those arguments,
+// hence a hit is always valid even if the allocation behind the pointer changed owner in between.
+using MapKey = std::array<long long, 8>;
+std::mutex g_map_mutex;
+std::map<MapKey, CUtensorMap> g_map_cache;
+
+template <typename Encode>
+bool cached_map(CUtensorMap* map, const MapKey& key, Encode&& encode) {
+  {
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) { *map = it->second; return true; }
+  }
+  if (!encode(map)) return false;
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  if (g_map_cache.size() >= 4096) g_map_cache.clear();
+  g_map_cache.emplace(key, *map);
+  return true;
+}
+
+bool encode_tensor_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows,
+                       bool f32) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return false;
   const int esz = f32 ? 4 : 2;
@@ -405,8 +429,14 @@ bool make_tensor_map(CUtensorMap* map, const void* base, long long rows, long lo
 }
 
 // Output map: [slabs][rows][slab_cols] (a plain matrix is one slab), boxes of 32 rows x 128 bytes.
-bool make_output_map(CUtensorMap* map, const void* base, long long rows, long long slab_cols, long long ld,
-                     long long slabs, long long slab_stride, bool f32) {
+bool make_tensor_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows,
+                     bool f32 = false) {
+  const MapKey key{0, reinterpret_cast<long long>(base), rows, cols, ld, box_rows, f32 ? 1 : 0, 0};
+  return cached_map(map, key, [&](CUtensorMap* m) { return encode_tensor_map(m, base, rows, cols, ld, box_rows, f32); });
+}
+
+bool encode_output_map(CUtensorMap* map, const void* base, long long rows, long long slab_cols, long long ld,
+                       long long slabs, long long slab_stride, bool f32) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return false;
   const int esz = f32 ? 4 : 2;
@@ -423,14 +453,35 @@ bool make_output_map(CUtensorMap* map, const void* base, long long rows, long lo
   return r == CUDA_SUCCESS;
 }
 
-int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return sms;
+// Per-device launch state.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize), the SM count and the number of
+// co-resident clusters are properties of ONE device: a process that drives several GPUs (one engine per device)
+// needs them per device ordinal, not per process.
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+  bool attr_set = false;
+  long long max_clusters = 0;
+};
+std::mutex g_device_mutex;
+
+bool make_output_map(CUtensorMap* map, const void* base, long long rows, long long slab_cols, long long ld,
+                     long long slabs, long long slab_stride, bool f32) {
+  const MapKey key{1, reinterpret_cast<long long>(base), rows, slab_cols, ld, slabs, slab_stride, f32 ? 1 : 0};
+  return cached_map(map, key, [&](CUtensorMap* m) {
+    return encode_output_map(m, base, rows, slab_cols, ld, slabs, slab_stride, f32);
+  });
+}
+
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
+int num_sms(int dev) {
+  static int sms[kMaxDevices] = {};
+  std::lock_guard<std::mutex> lock(g_device_mutex);
+  if (sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return sms[dev];
 }
 
 template <int CG, int BLOCK_N, int STAGES, int MC = 1>
@@ -446,34 +497,42 @@ int launch_variant(const GemmProblem& p, cudaStream_t stream, const char** err) 
     return TDC_ECUDA;
   }
   auto kernel = tdc_gemm_kernel<CG, BLOCK_N, STAGES, MC>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotalBytes) != cudaSuccess) {
-      if (err) *err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
-      return TDC_ECUDA;
+  const int dev = current_device();
+  const int sms = num_sms(dev);
+  static DeviceState state[kMaxDevices];  // per template instantiation AND per device
+  long long max_clusters;
+  {
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    DeviceState& st = state[dev];
+    if (!st.attr_set) {
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotalBytes) != cudaSuccess) {
+        if (err) *err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
+        return TDC_ECUDA;
+      }
+      st.attr_set = true;
     }
-    attr_set = true;
+    // persistent grid = as many clusters as can be co-resident (clusters of 4 do not tile the 148 SMs
+    // perfectly: GPCs have 16-20 SMs), otherwise the static tile striding would serialise the leftovers
+    if (st.max_clusters == 0) {
+      st.max_clusters = sms / (CG * MC);
+      if (CG * MC > 2) {
+        cudaLaunchConfig_t q{};
+        q.gridDim = dim3(static_cast<unsigned>(sms / (CG * MC) * CG * MC));
+        q.blockDim = dim3(kNumThreads);
+        q.dynamicSmemBytes = L::kTotalBytes;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = CG * MC; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+        q.attrs = qa; q.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kernel, &q) == cudaSuccess && n > 0 && n < st.max_clusters)
+          st.max_clusters = n;
+      }
+    }
+    max_clusters = st.max_clusters;
   }
   const long long m_tiles = (p.m + kBlockM * CG - 1) / (kBlockM * CG);
   const long long tiles = ((m_tiles + MC - 1) / MC) * ((p.n + BLOCK_N - 1) / BLOCK_N);
-  // persistent grid = as many clusters as can be co-resident (clusters of 4 do not tile the 148 SMs
-  // perfectly: GPCs have 16-20 SMs), otherwise the static tile striding would serialise the leftovers
-  static long long max_clusters = 0;  // per template instantiation
-  if (max_clusters == 0) {
-    max_clusters = num_sms() / (CG * MC);
-    if (CG * MC > 2) {
-      cudaLaunchConfig_t q{};
-      q.gridDim = dim3(static_cast<unsigned>(num_sms() / (CG * MC) * CG * MC));
-      q.blockDim = dim3(kNumThreads);
-      q.dynamicSmemBytes = L::kTotalBytes;
-      cudaLaunchAttribute qa[1];
-      qa[0].id = cudaLaunchAttributeClusterDimension;
-      qa[0].val.clusterDim.x = CG * MC; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-      q.attrs = qa; q.numAttrs = 1;
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, kernel, &q) == cudaSuccess && n > 0 && n < max_clusters) max_clusters = n;
-    }
-  }
   long long clusters = max_clusters;
   if (tiles < clusters) clusters = tiles;
   // L2 policy: W is re-read by every M tile -> evict_last; A and C stream.  (dev knob TDC_GEMM_HINTS=awc, one

@@ -77,8 +77,13 @@ __global__ void __launch_bounds__(256) frame_pair_partial_kernel(const void* __r
   }
 }
 
-// cos[pair] = dot / (max(|a|, eps) * max(|b|, eps))   (F.cosine_similarity, eps = 1e-8)
-__global__ void cosine_finish_kernel(const float* __restrict__ partial, int pairs, int slices, float* __restrict__ cos) {
+// cos[pair] = dot / (max(|a|, eps) * max(|b|, eps))   (F.cosine_similarity, eps = 1e-8), accumulated in fp32 and
+// then rounded to the features' own dtype: the reference evaluates F.cosine_similarity in the DINO feature dtype
+// (bf16 / fp16 under the model dtype) and argsorts those rounded values, so ties created by the rounding must
+// exist here too (they are broken by index, like a stable sort).  The intermediate roundings of torch's bf16
+// composition are not reproduced — only the final value's precision.
+__global__ void cosine_finish_kernel(const float* __restrict__ partial, int pairs, int slices, int dtype,
+                                     float* __restrict__ cos) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= pairs) return;
   float dot = 0.f, na = 0.f, nb = 0.f;
@@ -86,18 +91,23 @@ __global__ void cosine_finish_kernel(const float* __restrict__ partial, int pair
     const float* q = partial + (static_cast<size_t>(p) * slices + s) * 3;
     dot += q[0]; na += q[1]; nb += q[2];
   }
-  cos[p] = dot / (fmaxf(sqrtf(na), 1e-8f) * fmaxf(sqrtf(nb), 1e-8f));
+  float c = dot / (fmaxf(sqrtf(na), 1e-8f) * fmaxf(sqrtf(nb), 1e-8f));
+  if (dtype == TDC_BF16) c = __bfloat162float(__float2bfloat16_rn(c));
+  else if (dtype == TDC_F16) c = __half2float(__float2half_rn(c));
+  cos[p] = c;
 }
 
 // The k smallest values' indices, ascending by index (== sort(argsort(x)[:k])); ties broken by index.
+// NaN (inf/inf from overflowed fp16 features) ranks last, as in torch.argsort: the key is +inf, so at most k
+// flags are ever set and the store below cannot run past the k-element output.
 __global__ void __launch_bounds__(256) select_smallest_kernel(const float* __restrict__ x, int n, int k,
                                                               long long* __restrict__ out) {
   extern __shared__ unsigned char sel[];  // n flags
   for (int i = threadIdx.x; i < n; i += 256) {
-    const float xi = x[i];
+    const float xi = isnan(x[i]) ? INFINITY : x[i];
     int rank = 0;
     for (int j = 0; j < n; ++j) {
-      const float xj = x[j];
+      const float xj = isnan(x[j]) ? INFINITY : x[j];
       rank += (xj < xi) || (xj == xi && j < i);
     }
     sel[i] = rank < k;
@@ -107,7 +117,7 @@ __global__ void __launch_bounds__(256) select_smallest_kernel(const float* __res
     if (!sel[i]) continue;
     int pos = 0;
     for (int j = 0; j < i; ++j) pos += sel[j];
-    out[pos] = i;
+    if (pos < k) out[pos] = i;
   }
 }
 
@@ -124,7 +134,7 @@ int frame_cosine_launch(const void* feats, int dtype, int n_frames, long long di
   const int pairs = n_frames - 1;
   const int slices = frame_cosine_slices(dim);
   frame_pair_partial_kernel<<<dim3(pairs, slices), 256, 0, stream>>>(feats, dtype, dim, slices, partial_ws);
-  cosine_finish_kernel<<<(pairs + 127) / 128, 128, 0, stream>>>(partial_ws, pairs, slices, cos);
+  cosine_finish_kernel<<<(pairs + 127) / 128, 128, 0, stream>>>(partial_ws, pairs, slices, dtype, cos);
   const cudaError_t rc = cudaGetLastError();
   if (rc != cudaSuccess) {
     if (err) *err = cudaGetErrorString(rc);

@@ -112,7 +112,10 @@ class TDCBertModel(nn.Module):
         self.apply(self._init_weights)
         self._engine: Optional[QFormerEngine] = None
         self._engine_key = None
-        self.check_masks = True  # verify encoder_attention_mask is a prefix mask (costs one sync per call)
+        # Verify that encoder_attention_mask is a prefix mask.  Off by default: the check reads device data on
+        # the host (one sync per call, breaks CUDA-graph capture) and the reference only ever passes all-ones
+        # masks (cambrian_arch.py:1648-1650).  Turn it on when feeding hand-made masks.
+        self.check_masks = False
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_engine())
 
     def _init_weights(self, m):
@@ -135,11 +138,20 @@ class TDCBertModel(nn.Module):
         self._engine_key = None
         return out
 
+    def _weights_version(self) -> int:
+        """Cheap fingerprint of in-place edits: every parameter's autograd version counter."""
+        return sum(int(p._version) for p in self.parameters())
+
     def engine(self, d_out: int = 0, extra_state=None, extra_key=None) -> QFormerEngine:
         """The libtdc handle holding this module's weights (rebuilt when they move/change).
-        `extra_state` adds sibling tensors (vision_proj.*); `extra_key` identifies their version."""
+        `extra_state` adds sibling tensors (vision_proj.*); `extra_key` identifies their version.
+        A handle that carries vision_proj also serves the plain `.bert(...)` forward (d_out = 0 requests reuse
+        it), so alternating `Qformer.bert(...)` and `TDCCompressor.compress_video(...)` keeps ONE handle."""
         p = self.embeddings.LayerNorm.weight
-        key = (p.device, d_out, extra_key)
+        if d_out == 0 and extra_state is None and self._engine is not None and self._engine_key is not None \
+                and self._engine_key[0] == p.device and self._engine_key[3] == self._weights_version():
+            return self._engine
+        key = (p.device, d_out, extra_key, self._weights_version())
         if self._engine is None or self._engine_key != key:
             if p.device.type != "cuda":
                 raise RuntimeError("TDCBertModel runs on a CUDA (sm_100a) device only: move the module to the GPU; "

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 def _metrics_ok(test, ref, what):
     m = oracle.parity_metrics(test.float().cpu(), ref)
     print(what, m)
-    assert m["min_cos"] >= 0.999 and m["max_abs_over_max_ref"] <= 2e-2, (what, m)
+    assert m["min_cos"] >= 0.999 and m["max_abs_over_max_ref"] <= 2e-2 and m["max_tok_rel_l2"] <= 2e-2, (what, m)
 
 
 def _small_cfg(**kw):

@@ -62,7 +62,7 @@ def test_stage_matches_the_reference_driver(path):
     ref_frames = driver_frames(w, sig, dino)
     assert frames.shape == ref_frames.shape == (n, 156, DRIVER_D)
     fm = oracle.parity_metrics(frames.float().cpu(), ref_frames)
-    assert fm["min_cos"] >= 0.999 and fm["max_abs_over_max_ref"] <= 2e-2, fm
+    assert fm["min_cos"] >= 0.999 and fm["max_abs_over_max_ref"] <= 2e-2 and fm["max_tok_rel_l2"] <= 2e-2, fm
     assert torch.equal(frames.view(n, 12, 13, DRIVER_D)[:, :, 12].cpu(),
                        torch.from_numpy(w["image_newline"]).expand(n, 12, DRIVER_D))
 
@@ -79,7 +79,7 @@ def test_stage_matches_the_reference_driver(path):
     assert tuple(seq.shape) == tuple(ref.shape)
     mt = oracle.parity_metrics(seq.float().cpu(), ref)
     print(os.path.basename(path), mt)
-    assert mt["min_cos"] >= 0.999 and mt["max_abs_over_max_ref"] <= 2e-2, mt
+    assert mt["min_cos"] >= 0.999 and mt["max_abs_over_max_ref"] <= 2e-2 and mt["max_tok_rel_l2"] <= 2e-2, mt
 
 
 def test_append_newline_tokens_layout():

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 def _check(test, ref, what):
     m = qformer_oracle.parity_metrics(test.float().cpu(), ref)
     print(what, m)
-    assert m["min_cos"] >= 0.999 and m["max_abs_over_max_ref"] <= 2e-2, (what, m)
+    assert m["min_cos"] >= 0.999 and m["max_abs_over_max_ref"] <= 2e-2 and m["max_tok_rel_l2"] <= 2e-2, (what, m)
 
 
 def _module(hidden, dims, sides, layers, Q, sd):
