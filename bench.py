@@ -265,7 +265,10 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=96, help="rows per CPU batch (cpu_baseline / reference arm)")
     ap.add_argument("--cpu-passes", type=int, default=0,
                     help="passes over the CPU sample (default: 16 for cpu_baseline = about 10-20 s, 2 per reference-arm step)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--strong-steps", type=int, default=5, help="N > 1: timed steps of the strong-scaling sub-record")
+    ap.add_argument("--parity-rows", type=int, default=4,
+                    help="rows of the timed workload re-checked against the CPU oracle after the run (0 = skip)")
     ap.add_argument("--e2e-rows-per-batch", type=int, default=600,
                     help="row batch of the host-streaming leg (smaller = shorter pipeline fill/drain; the leg is PCIe-bound)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -427,6 +430,83 @@ def main():
     ms_step = float(t.item()) / args.steps
     value = world * S / (ms_step * 1e-3)
 
+    # ---- the exchange verifies itself: every rank's locally computed rows, all-gathered by NCCL, must equal
+    # bit for bit what the timed step left in the gather buffer on EVERY rank (multicast stores + device barrier,
+    # or the per-batch NCCL all-gathers) — rows are independent, so batching cannot change a bit
+    exchange_check = None
+    strong = None
+    if world > 1:
+        final = step()
+        barrier()
+        local_all = compute(enc, qs_dev, ts_dev)
+        ref_gather = torch.empty((world * rows, K, d_out), dtype=torch.bfloat16, device=dev)
+        dist.all_gather_into_tensor(ref_gather, local_all.contiguous())
+        ok = torch.equal(final.reshape(world * rows, K, d_out), ref_gather)
+        flag = torch.tensor([int(ok)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        exchange_check = bool(flag.item())
+        del ref_gather, local_all, final
+
+        # ---- strong scaling (BASELINE config 4): ONE video of S segments sharded over the N GPUs, S/N contiguous
+        # video-seconds per GPU, the same fused exchange; reference point = one GPU compressing all S segments
+        # (no exchange), timed in the same run on every rank (max over ranks, like everything else)
+        rows_s = rows // world
+        sb = [(rows_s * b // nb, rows_s * (b + 1) // nb) for b in range(nb)]
+        mc_s, gath_s = None, None
+        if mcast is not None:
+            from tdc_video_b200.dist import MulticastGather
+            mc_s = MulticastGather(rows_s, (K, d_out), torch.bfloat16, dev)
+        else:
+            gath_s = torch.empty((world, rows_s, K, d_out), dtype=torch.bfloat16, device=dev)
+        lo = rank * rows_s                         # this rank's range of the video
+
+        def strong_step():
+            if mc_s is not None:
+                for r0, r1 in sb:
+                    eng.compress_multicast(q_dev, enc[lo + r0:lo + r1], mc_s.slot_ptr(r0), ids_dev,
+                                           query_set=qs_dev[lo + r0:lo + r1],
+                                           text_set=None if ts_dev is None else ts_dev[lo + r0:lo + r1],
+                                           out_dtype=torch.bfloat16)
+                mc_s.barrier()
+                return mc_s.gathered
+            works = []
+            for r0, r1 in sb:
+                o = compute(enc[lo + r0:lo + r1], qs_dev[lo + r0:lo + r1],
+                            None if ts_dev is None else ts_dev[lo + r0:lo + r1])
+                works.append(dist.all_gather([gath_s[w_, r0:r1] for w_ in range(world)], o, async_op=True))
+            for wk in works:
+                wk.wait()
+            return gath_s.view(world * rows_s, K, d_out)
+
+        def timed(fn, n):
+            for _ in range(2):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            barrier()
+            tt = torch.tensor([a.elapsed_time(b) / n], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
+        strong_ms = timed(strong_step, args.strong_steps)
+        n1_ms = timed(lambda: compute(enc, qs_dev, ts_dev), max(2, args.strong_steps // 2))
+        # the sharded video equals the same rows compressed by one GPU (rank 0's copy of the check: its own range)
+        mine_s = compute(enc[lo:lo + rows_s], qs_dev[lo:lo + rows_s], None if ts_dev is None else ts_dev[lo:lo + rows_s])
+        got = strong_step().reshape(world, rows_s, K, d_out)[rank]
+        flag = torch.tensor([int(torch.equal(got, mine_s))], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        strong = {"segments_total": S, "segments_per_gpu": S // world, "rows_per_gpu": rows_s, "ms_per_step": strong_ms,
+                  "value": S / (strong_ms * 1e-3), "unit": "video-s/s", "one_gpu_ms_per_step": n1_ms,
+                  "speedup_vs_n1": n1_ms / strong_ms, "steps": args.strong_steps, "exchange": exchange,
+                  "own_rows_match": bool(flag.item()),
+                  "limiter": "per-GPU step = compute of S/N segments + device barrier closing the multicast exchange; "
+                             "every GPU is power-capped and the step follows the slowest one"}
+        del mc_s, gath_s
+
     # ---- end to end: KV tokens in pinned host memory, result back in host memory
     e2e = None
     if not args.no_e2e:
@@ -477,6 +557,8 @@ def main():
                    "l2": f"inputs {enc.numel() * 2 / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
                    "accumulate": "fp32 (TMEM), LN/softmax/residual fp32"},
         "clocks": clocks,
+        "exchange_check": exchange_check,
+        "strong": strong,
         "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": {"kernel": "tdc_gemm_kernel (cross-attn K/V projection, all 6 layers, N=9216)", "bound": "tensor",
@@ -494,6 +576,18 @@ def main():
                  "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}},
         "ranks": per_rank,
     }
+    if args.parity_rows > 0 and mlp is None:
+        # the timed workload's own rows against the CPU oracle (checker only): the first rows of this rank's video
+        from oracle import qformer_oracle as oracle
+        n_chk = min(args.parity_rows, rows)
+        got = compute(enc[:n_chk], qs_dev[:n_chk], None if ts_dev is None else ts_dev[:n_chk]).float().cpu()
+        sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
+        ids_chk = None if ids_dev is None else ids_dev.cpu().expand(n_chk, -1)
+        ref = oracle.compress(sd_t, geom, q_sets[query_set[:n_chk].long()], enc_host[:n_chk].float(), ids_chk)
+        pm = oracle.parity_metrics(got, ref)
+        line["parity_sample"] = dict(rows=n_chk, num_query=K, **pm,
+                                     ok=bool(pm["min_cos"] >= 0.999 and pm["max_abs_over_max_ref"] <= 2e-2
+                                             and pm["max_tok_rel_l2"] <= 2e-2))
     if not args.no_cpu_baseline:
         passes = args.cpu_passes or 16
         v, dt, cores = cpu_baseline(geom, sd, w, args.cpu_sample_rows, 99, passes)
