@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(128, 4) tdc_attention_kernel(AttentionArgs a) 
   const int qb = static_cast<int>((wid / a.heads) % nqb);
   const int r = static_cast<int>(wid / (static_cast<long long>(a.heads) * nqb));
 
-  const int kv_total = a.kv_seg1 + a.kv_seg2;
+  const int kv_total = a.kv_seg1 + a.kv_seg2 + a.kv_seg3;
   const uint32_t mbits = a.kv_mask != nullptr ? a.kv_mask[r] : 0xffffffffu;
   int kvn = kv_total;
   if (a.kv_len != nullptr) {
@@ -109,7 +109,9 @@ __global__ void __launch_bounds__(128, 4) tdc_attention_kernel(AttentionArgs a) 
     vbase += first * a.ldv;
   }
   auto kv_row = [&](int t) -> long long {
-    return kTwoSeg ? seg_row(r, t, a.kv_seg1, a.kv_seg2, a.kv_base1, a.kv_base2) : static_cast<long long>(t);
+    if (!kTwoSeg) return static_cast<long long>(t);
+    if (t >= a.kv_seg1 + a.kv_seg2) return a.kv_base3 + (t - a.kv_seg1 - a.kv_seg2);  // shared by all rows
+    return seg_row(r, t, a.kv_seg1, a.kv_seg2, a.kv_base1, a.kv_base2);
   };
   extern __shared__ uint4 kv_ring[];  // [4 warps][kStages][8 chunks][32 lanes]
   uint4* ring = kv_ring + (threadIdx.x >> 5) * (kStages * kSlotsPerStage) + lane;
@@ -258,11 +260,11 @@ __global__ void __launch_bounds__(128, 4) tdc_attention_kernel(AttentionArgs a) 
 }  // namespace
 
 int attention_launch(const AttentionArgs& a, cudaStream_t stream, const char** err) {
-  if (a.rows <= 0 || a.nq <= 0 || a.heads <= 0 || a.kv_seg1 + a.kv_seg2 <= 0) {
+  if (a.rows <= 0 || a.nq <= 0 || a.heads <= 0 || a.kv_seg1 + a.kv_seg2 + a.kv_seg3 <= 0) {
     if (err) *err = "attention: empty problem";
     return TDC_EINVAL;
   }
-  if (a.kv_mask != nullptr && a.kv_seg1 + a.kv_seg2 > 32) {
+  if (a.kv_mask != nullptr && a.kv_seg1 + a.kv_seg2 + a.kv_seg3 > 32) {
     if (err) *err = "attention: kv_mask supports at most 32 KV tokens per row";
     return TDC_EINVAL;
   }
@@ -291,7 +293,7 @@ int attention_launch(const AttentionArgs& a, cudaStream_t stream, const char** e
       attr_set[dev] = true;
     }
   }
-  if (a.q_seg2 > 0 || a.kv_seg2 > 0)
+  if (a.q_seg2 > 0 || a.kv_seg2 > 0 || a.kv_seg3 > 0)
     tdc_attention_kernel<true><<<static_cast<unsigned>(blocks), 128, kSmem, stream>>>(a);
   else
     tdc_attention_kernel<false><<<static_cast<unsigned>(blocks), 128, kSmem, stream>>>(a);

@@ -1,0 +1,232 @@
+// Kernels of the upstream ("frames") entry of the TDC path: everything between the towers' outputs and the
+// Q-Former that is not a GEMM.  Reference: tdc/cambrian_arch.py:1149-1150 (mm_projector on every frame
+// token), :1269-1281 (image_newline closes every row of the token grid), :1611-1614 (audio_proj tokens
+// appended to every frame), :1629-1640 (queries = avg-pool of the key frame through query_proj).
+//
+// All of them are plain HBM-bound data movement (16-byte vectors, one read + one write of their operand);
+// the fold helpers (transpose, matvec) run once per weight load.
+#include "tdc_kernels.cuh"
+#include "tdc_ptx.cuh"
+
+namespace tdc {
+
+namespace {
+
+// dst block i = src block idx[i]; a block is `vecs` 16-byte vectors (one frame's tokens).
+__global__ void __launch_bounds__(256) gather_blocks_kernel(const uint4* __restrict__ src, const int32_t* __restrict__ idx,
+                                                            uint4* __restrict__ dst, long long vecs) {
+  const long long item = blockIdx.y;
+  const uint4* s = src + static_cast<long long>(idx[item]) * vecs;
+  uint4* d = dst + item * vecs;
+  for (long long v = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; v < vecs;
+       v += static_cast<long long>(gridDim.x) * 256)
+    d[v] = __ldg(s + v);
+}
+
+// out[c, r] = in[r, c] (bf16), 32x32 tiles through shared memory.
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int rows, int cols,
+                                                             __nv_bfloat16* __restrict__ out) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    if (r < rows && c < cols) tile[j][tx] = in[static_cast<long long>(r) * cols + c];
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (r < rows && c < cols) out[static_cast<long long>(c) * rows + r] = tile[tx][j];
+  }
+}
+
+// y[n] = sum_k W[n, k] * x[k] + b[n]   (W bf16 [n, k], x / b / y fp32); one warp per output.
+__global__ void __launch_bounds__(256) matvec_bias_kernel(const __nv_bfloat16* __restrict__ w, const float* __restrict__ x,
+                                                          const float* __restrict__ b, float* __restrict__ y, int n,
+                                                          int k) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  const __nv_bfloat16* wr = w + static_cast<long long>(row) * k;
+  float acc = 0.f;
+  for (int j = lane * 2; j < k; j += 64) {
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(wr + j);
+    acc = fmaf(__low2float(v), x[j], acc);
+    acc = fmaf(__high2float(v), x[j + 1], acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) y[row] = acc + (b != nullptr ? b[row] : 0.f);
+}
+
+// Token u of a frame's sequence with newline tokens: grid row g = u / (side + 1), column j = u % (side + 1);
+// j < side -> visual token g * side + j, j == side -> the image_newline vector.
+// adaptive_avg_pool1d over that sequence (bins [floor(i*L/K), ceil((i+1)*L/K)), L = side * (side + 1)).
+__global__ void __launch_bounds__(256) pool_static_queries_kernel(const __nv_bfloat16* __restrict__ xv,
+                                                                  const float* __restrict__ newline, int side, int d,
+                                                                  int num_query, __nv_bfloat16* __restrict__ out) {
+  const int c = blockIdx.x / num_query, i = blockIdx.x % num_query;
+  const int L = side * (side + 1);
+  const int start = static_cast<int>((static_cast<long long>(i) * L) / num_query);
+  const int end = static_cast<int>((static_cast<long long>(i + 1) * L + num_query - 1) / num_query);
+  const float inv = 1.0f / static_cast<float>(end - start);
+  const __nv_bfloat16* frame = xv + static_cast<long long>(c) * side * side * d;
+  for (int j = threadIdx.x; j < d / 4; j += 256) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = start; u < end; ++u) {
+      const int g = u / (side + 1), col = u % (side + 1);
+      float4 v;
+      if (col < side) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(frame + static_cast<long long>(g * side + col) * d) + j);
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+        v = make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+      } else {
+        // the reference pools the model-dtype (bf16) copy of the parameter
+        const float4 nl = __ldg(reinterpret_cast<const float4*>(newline) + j);
+        v = make_float4(__bfloat162float(__float2bfloat16_rn(nl.x)), __bfloat162float(__float2bfloat16_rn(nl.y)),
+                        __bfloat162float(__float2bfloat16_rn(nl.z)), __bfloat162float(__float2bfloat16_rn(nl.w)));
+      }
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    uint2 pk;
+    pk.x = pack_bf16x2(acc.x * inv, acc.y * inv);
+    pk.y = pack_bf16x2(acc.z * inv, acc.w * inv);
+    reinterpret_cast<uint2*>(out + (static_cast<long long>(c) * num_query + i) * d)[j] = pk;
+  }
+}
+
+// static_out[c] = [ (side visual tokens, newline) x side | Ta audio tokens ]  in out_dtype (bf16 / fp16 / fp32)
+__global__ void __launch_bounds__(256) assemble_static_kernel(const __nv_bfloat16* __restrict__ xv,
+                                                              const __nv_bfloat16* __restrict__ xa,
+                                                              const float* __restrict__ newline, int chunks, int side,
+                                                              int ta, int d, void* __restrict__ out, int out_dtype) {
+  const int ls = side * (side + 1) + ta;
+  const long long tok = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const long long c = tok / ls;
+  const int u = static_cast<int>(tok % ls);
+  if (c >= chunks) return;
+  const int lane = threadIdx.x & 31;
+  const __nv_bfloat16* src = nullptr;
+  if (u < side * (side + 1)) {
+    const int g = u / (side + 1), col = u % (side + 1);
+    if (col < side) src = xv + (c * side * side + g * side + col) * d;
+  } else {
+    src = xa + (c * ta + (u - side * (side + 1))) * d;
+  }
+  const size_t esz = out_dtype == TDC_F32 ? 4 : 2;
+  uint8_t* dst = static_cast<uint8_t*>(out) + static_cast<size_t>(tok) * d * esz;
+  for (int j = lane; j < d / 4; j += 32) {
+    float4 v;
+    if (src != nullptr) {
+      const uint2 raw = __ldg(reinterpret_cast<const uint2*>(src) + j);
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+      const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+      v = make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+    } else {
+      v = __ldg(reinterpret_cast<const float4*>(newline) + j);
+    }
+    if (out_dtype == TDC_F32) {
+      reinterpret_cast<float4*>(dst)[j] = v;
+    } else if (out_dtype == TDC_BF16) {
+      uint2 pk;
+      pk.x = pack_bf16x2(v.x, v.y);
+      pk.y = pack_bf16x2(v.z, v.w);
+      reinterpret_cast<uint2*>(dst)[j] = pk;
+    } else {
+      const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+      reinterpret_cast<uint2*>(dst)[j] = pk;
+    }
+  }
+}
+
+// rows [row0, row0 + count) of every slab = the slab's fp32 source vector (bf16): the K/V of the newline tokens
+__global__ void __launch_bounds__(256) broadcast_rows_kernel(const float* __restrict__ src, int width, int slabs,
+                                                             __nv_bfloat16* __restrict__ dst, long long slab_stride,
+                                                             long long row0, int count) {
+  const int slab = blockIdx.y;
+  const float* s = src + static_cast<long long>(slab) * width;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < count * width; e += gridDim.x * 256) {
+    const int r = e / width, c = e % width;
+    dst[slab * slab_stride + (row0 + r) * width + c] = __float2bfloat16_rn(s[c]);
+  }
+}
+
+int launched(const char** err) {
+  const cudaError_t rc = cudaGetLastError();
+  if (rc != cudaSuccess) {
+    if (err) *err = cudaGetErrorString(rc);
+    return TDC_ECUDA;
+  }
+  return TDC_OK;
+}
+
+}  // namespace
+
+int gather_blocks_launch(const void* src, const int32_t* idx, void* dst, long long items, long long block_bytes,
+                         cudaStream_t stream, const char** err) {
+  if (items <= 0) return TDC_OK;
+  if (block_bytes % 16 != 0 || items > 65535) {
+    if (err) *err = "gather_blocks: block size must be a multiple of 16 bytes and at most 65535 blocks per call";
+    return TDC_EINVAL;
+  }
+  const long long vecs = block_bytes / 16;
+  int bx = static_cast<int>((vecs + 255) / 256);
+  if (bx > 32) bx = 32;
+  gather_blocks_kernel<<<dim3(bx, static_cast<unsigned>(items)), 256, 0, stream>>>(
+      static_cast<const uint4*>(src), idx, static_cast<uint4*>(dst), vecs);
+  return launched(err);
+}
+
+int transpose_bf16_launch(const __nv_bfloat16* in, int rows, int cols, __nv_bfloat16* out, cudaStream_t stream,
+                          const char** err) {
+  transpose_bf16_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), 256, 0, stream>>>(in, rows, cols, out);
+  return launched(err);
+}
+
+int matvec_bias_launch(const __nv_bfloat16* w, const float* x, const float* b, float* y, int n, int k,
+                       cudaStream_t stream, const char** err) {
+  if (k % 2 != 0) {
+    if (err) *err = "matvec: k must be even";
+    return TDC_EINVAL;
+  }
+  matvec_bias_kernel<<<(n + 7) / 8, 256, 0, stream>>>(w, x, b, y, n, k);
+  return launched(err);
+}
+
+int pool_static_queries_launch(const __nv_bfloat16* xv, const float* newline, int chunks, int side, int d,
+                               int num_query, __nv_bfloat16* out, cudaStream_t stream, const char** err) {
+  if (chunks <= 0) return TDC_OK;
+  if (d % 4 != 0) {
+    if (err) *err = "pool_static_queries: d must be a multiple of 4";
+    return TDC_EINVAL;
+  }
+  pool_static_queries_kernel<<<static_cast<unsigned>(chunks * num_query), 256, 0, stream>>>(xv, newline, side, d,
+                                                                                           num_query, out);
+  return launched(err);
+}
+
+int assemble_static_launch(const __nv_bfloat16* xv, const __nv_bfloat16* xa, const float* newline, int chunks, int side,
+                           int ta, int d, void* out, int out_dtype, cudaStream_t stream, const char** err) {
+  if (chunks <= 0) return TDC_OK;
+  const long long toks = static_cast<long long>(chunks) * (side * (side + 1) + ta);
+  if (d % 4 != 0) {
+    if (err) *err = "assemble_static: d must be a multiple of 4";
+    return TDC_EINVAL;
+  }
+  assemble_static_kernel<<<static_cast<unsigned>((toks + 7) / 8), 256, 0, stream>>>(xv, xa, newline, chunks, side, ta, d,
+                                                                                    out, out_dtype);
+  return launched(err);
+}
+
+int broadcast_rows_launch(const float* src, int width, int slabs, __nv_bfloat16* dst, long long slab_stride,
+                          long long row0, int count, cudaStream_t stream, const char** err) {
+  if (count <= 0 || slabs <= 0) return TDC_OK;
+  broadcast_rows_kernel<<<dim3(8, slabs), 256, 0, stream>>>(src, width, slabs, dst, slab_stride, row0, count);
+  return launched(err);
+}
+
+}  // namespace tdc

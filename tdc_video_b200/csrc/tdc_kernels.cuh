@@ -14,6 +14,8 @@ namespace tdc {
 // and the text-only FFN (:455-462) are plain dense GEMMs over contiguous rows.
 // Token i of row r lives at slab row
 //     i <  seg1 ?  base1 + r*seg1 + i  :  base2 + r*seg2 + (i - seg1).
+// KV tokens may have a third segment of kv_seg3 tokens SHARED by all rows (slab rows kv_base3 ...): the
+// image_newline tokens of a frame, whose K/V are the same for every frame (cambrian_arch.py:1269-1281).
 struct AttentionArgs {
   const __nv_bfloat16* q = nullptr;  // head h of a token at q + row*ldq + h*64
   const __nv_bfloat16* k = nullptr;
@@ -24,8 +26,8 @@ struct AttentionArgs {
   int nq = 0;  // queries per row (= q_seg1 + q_seg2)
   int q_seg1 = 0, q_seg2 = 0;
   long long q_base1 = 0, q_base2 = 0;
-  int kv_seg1 = 0, kv_seg2 = 0;
-  long long kv_base1 = 0, kv_base2 = 0;
+  int kv_seg1 = 0, kv_seg2 = 0, kv_seg3 = 0;
+  long long kv_base1 = 0, kv_base2 = 0, kv_base3 = 0;
   const int32_t* kv_len = nullptr;  // [rows] or null
   const uint32_t* kv_mask = nullptr;  // [rows] or null: bit j = KV token j may be attended (needs <= 32 KV tokens)
   float scale_log2 = 0.f;           // log2(e) / sqrt(head size)
@@ -85,6 +87,26 @@ int take_query_tokens_launch(const void* hidden, int dtype, int rows, int tokens
 // adaptive_avg_pool1d over the token axis: bins [floor(i*L/K), ceil((i+1)*L/K)) (tdc/cambrian_arch.py:1633-1637)
 int avg_pool_tokens_launch(const void* frames, int dtype, int n, int tokens, int d, int num_query,
                            __nv_bfloat16* out, cudaStream_t stream, const char** err);
+
+// ---- upstream ("frames") entry: frontend.cu -------------------------------------------------------------
+// dst block i = src block idx[i] (blocks of block_bytes, a multiple of 16): frames gathered by role (static / dynamic)
+int gather_blocks_launch(const void* src, const int32_t* idx, void* dst, long long items, long long block_bytes,
+                         cudaStream_t stream, const char** err);
+int transpose_bf16_launch(const __nv_bfloat16* in, int rows, int cols, __nv_bfloat16* out, cudaStream_t stream,
+                          const char** err);
+// y = W x + b (W bf16 [n, k]; x, b, y fp32) — weight folding at load time
+int matvec_bias_launch(const __nv_bfloat16* w, const float* x, const float* b, float* y, int n, int k,
+                       cudaStream_t stream, const char** err);
+// adaptive_avg_pool1d over [side x (side visual tokens + newline)] of every key frame (cambrian_arch.py:1633-1637
+// on the newline-extended frame of :1269-1281): xv [chunks, side*side, d] bf16 -> out [chunks, K, d] bf16
+int pool_static_queries_launch(const __nv_bfloat16* xv, const float* newline, int chunks, int side, int d,
+                               int num_query, __nv_bfloat16* out, cudaStream_t stream, const char** err);
+// static_out[c] = [(side visual tokens, newline) x side | ta audio tokens] (the key frame as it passes through)
+int assemble_static_launch(const __nv_bfloat16* xv, const __nv_bfloat16* xa, const float* newline, int chunks, int side,
+                           int ta, int d, void* out, int out_dtype, cudaStream_t stream, const char** err);
+// rows [row0, row0 + count) of each of `slabs` matrices [*, width] (slab_stride elements apart) = src[slab] as bf16
+int broadcast_rows_launch(const float* src, int width, int slabs, __nv_bfloat16* dst, long long slab_stride,
+                          long long row0, int count, cudaStream_t stream, const char** err);
 
 // Adaptive segmentation (tdc/cambrian_arch.py:832-849): cos[i] = cosine_similarity(frame i, frame i+1) over
 // the flattened feature dim; partial_ws holds (n_frames-1) * frame_cosine_slices(dim) * 3 floats.

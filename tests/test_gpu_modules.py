@@ -203,12 +203,17 @@ def test_adapt_segment_matches_oracle(n_frames, dtype):
     if cos_o is None:
         assert cos is None and torch.equal(seg.cpu(), seg_o)
     else:
-        assert torch.allclose(cos.cpu(), cos_o, atol=1e-3)
+        # the library rounds the similarities to the feature dtype, as the reference's F.cosine_similarity on
+        # bf16 / fp16 features does (half a bf16 ulp below 1.0 = 2e-3)
+        tol = 1e-3 if dtype == torch.float32 else 3e-3
+        assert torch.allclose(cos.cpu(), cos_o, atol=tol)
+        if dtype != torch.float32:
+            assert torch.equal(cos.cpu(), cos.cpu().to(dtype).float())
         # the 24 chosen similarities must be separated from the rest by more than the tolerance for the
         # index comparison to be meaningful
         srt = torch.sort(cos_o).values
         if len(srt) > 24:
-            assert float(srt[24] - srt[23]) > 2e-3
+            assert float(srt[24] - srt[23]) > 2 * tol
         assert torch.equal(seg.cpu(), seg_o)
     assert sum(segment_sizes(seg, len(sel))) == len(sel)
 
