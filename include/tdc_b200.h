@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TDC_B200_ABI_VERSION 1
+#define TDC_B200_ABI_VERSION 2
 
 typedef enum tdc_status {
   TDC_OK = 0,
@@ -62,7 +62,9 @@ typedef struct tdc_config {
   int32_t max_pos;           /* position-embedding rows (512) */
   float ln_eps;              /* layer_norm_eps (1e-12) */
   int32_t gemm_cta_group;    /* 0 = default, 1 = single-CTA tcgen05 tiles, 2 = CTA-pair tiles */
-  int32_t reserved[5];
+  int32_t d_frame_in;        /* mm_projector.0 in_features (1024 * towers); 0 = no upstream ("frames") entry */
+  int32_t d_audio;           /* audio_proj in_features (768, BEATs); 0 = no audio */
+  int32_t reserved[3];
 } tdc_config;
 
 /* One reference tensor (as stored in the reference state_dict, row-major). */
@@ -139,6 +141,51 @@ int tdc_compress_multicast(tdc_handle* h, const void* query_embeds, int32_t quer
                            int32_t num_text, void* out_multicast, int32_t out_dtype, void* workspace,
                            size_t workspace_bytes, tdc_stream_t stream);
 
+/* ---- the upstream entry: from the towers' outputs --------------------------------- */
+/* replaces, for ALL chunks of a video in one call (tdc/cambrian_arch.py):
+ *   :1149-1150  image_features = mm_projector(cat(tower features))            (Linear . GELU . Linear)
+ *   :1269-1281  image_newline appended to every row of the token grid
+ *   :1611-1614  audio_proj(audio_chunk_feature) concatenated to every frame's tokens
+ *   :1629-1640  query_tokens = query_proj(adaptive_avg_pool1d(key_frame)) | the learned query_tokens
+ *   :1653-1667  Qformer.bert(...) -> F.normalize(vision_proj(h[:, :K]))
+ * needs the handle created with d_frame_in > 0 (and d_audio > 0 for audio), d_enc == d_out, and the extra
+ * tensors `mm_projector.{0,2}.{weight,bias}`, `image_newline`, `query_proj.{weight,bias}`,
+ * [`audio_proj.{weight,bias}`], [`query_tokens`] passed to tdc_load_weights.
+ *
+ * A chunk is <= 8 consecutive frames of one segment (:1606): its first frame is the key ("static") frame, the
+ * others are rows.  The caller passes the integer plan (the reference builds it in its Python loop).
+ *   fold = 1: dynamic frames use weights folded at load time (K/V weights x mm_projector.2 / audio_proj; the
+ *             newline tokens' K/V are constants), so their d_llm-wide tokens are never materialised;
+ *   fold = 0: every projection runs as the reference orders them.
+ * Cross-attention does not depend on the order of its KV tokens, so both modes keep a row's tokens as
+ * [visual | audio | newline] instead of the reference's row-interleaved newlines. */
+typedef struct tdc_frames_args {
+  const void* frames;            /* [n_frames, Tv, d_frame_in] bf16: input of mm_projector; Tv = side*side */
+  const void* audio;             /* [n_frames, Ta, d_audio] bf16 per-frame audio tokens, or NULL (Ta = 0) */
+  const int32_t* static_frames;  /* [n_chunks] frame index of every chunk's key frame */
+  const int32_t* row_frames;     /* [rows]     frame index of every dynamic frame */
+  const int32_t* row_chunk;      /* [rows]     chunk of every row (its query set) */
+  const int64_t* input_ids;      /* [1, num_text] prompt shared by all rows, or NULL */
+  int32_t n_frames, n_chunks, rows;
+  int32_t visual_tokens;         /* Tv (144) */
+  int32_t audio_tokens;          /* Ta (50) or 0 */
+  int32_t num_query;             /* K */
+  int32_t num_text;              /* T */
+  int32_t learned_queries;       /* 1: queries = loaded `query_tokens` (query_type "learned") */
+  int32_t fold;
+  int32_t multicast;             /* 1: `out` is an NVSwitch multicast address (see tdc_compress_multicast) */
+  int32_t out_dtype;             /* dtype of out and static_out */
+  void* static_out;              /* [n_chunks, side*(side+1) + Ta, d_out] the key frames as they pass through, or NULL */
+  void* out;                     /* [rows, K, d_out] compressed tokens */
+} tdc_frames_args;
+
+/* Workspace for tdc_compress_frames processing `batch` rows (and key frames) at a time; any size from
+ * batch = 1 upwards works — the call sizes its internal batches to what it is given. */
+size_t tdc_frames_workspace_bytes(const tdc_handle* h, int32_t n_chunks, int32_t rows, int32_t batch,
+                                  int32_t visual_tokens, int32_t audio_tokens, int32_t num_query, int32_t num_text);
+int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* workspace, size_t workspace_bytes,
+                        tdc_stream_t stream);
+
 /* ---- small dense helpers on the same path ---------------------------------------- */
 /* replaces: nn.Linear forward — query_proj / audio_proj / vision_proj as plain callables
  * (cambrian_arch.py:1613,1638,1665).  y[m, n] = x[m, k] . w[n, k]^T + bias.
@@ -199,7 +246,8 @@ enum {
   TDC_K_QUERY_GEMM = 1, /* all query-side GEMMs */
   TDC_K_ATTENTION = 2,  /* self + cross short-query attention */
   TDC_K_ROWOPS = 3,     /* LayerNorm / embeddings / L2-normalise / converts */
-  TDC_K_COUNT = 4
+  TDC_K_FRONTEND = 4,   /* upstream entry: mm_projector / audio_proj / query_proj GEMMs, gathers, pooling, assembly */
+  TDC_K_COUNT = 5
 };
 int tdc_set_profiling(tdc_handle* h, int32_t enabled);
 /* Sums (ms) and launch counts since the last reset; synchronises the recorded events. */

@@ -120,7 +120,12 @@ def run_reference_driver(weights, geom, n_frames, *, d_llm, context_token_num=16
         max_num_segments=24, lowres_token=8, tokenizer_padding_side="right", hidden_size=d_llm)
     towers = [_StubTower(c1, t(siglip_table)), _StubTower(c2, t(dino_table))]
     inner.get_vision_tower_aux_list = lambda: towers
-    inner.mm_projector = linear("mm_projector", c1 + c2, d_llm)
+    if "mm_projector.0.weight" in weights:
+        # the shipped projector: Linear -> GELU -> Linear (multimodal_projector/builder.py:40-47, cambrian_arch.py:65-69)
+        inner.mm_projector = nn.Sequential(linear("mm_projector.0", c1 + c2, d_llm), nn.GELU(),
+                                           linear("mm_projector.2", d_llm, d_llm))
+    else:
+        inner.mm_projector = linear("mm_projector", c1 + c2, d_llm)
     inner.Qformer = qformer
     inner.query_tokens = nn.Parameter(t(weights["query_tokens"]))
     inner.vision_proj = linear("vision_proj", geom.hidden, d_llm)

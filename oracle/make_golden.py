@@ -125,11 +125,28 @@ def driver_tables(seed, n):
     return base, dino.astype(np.float32)
 
 
+def driver_weights_mlp(seed, K):
+    """driver_weights with the shipped GELU-MLP projector (`mm_projector.0.*`, `mm_projector.2.*`) instead of the
+    single Linear: the weights of the upstream ("frames") entry."""
+    w = driver_weights(seed, K)
+    del w["mm_projector.weight"], w["mm_projector.bias"]
+    rs = np.random.RandomState(seed + 1000)
+    f = lambda *s: (rs.standard_normal(s) * 0.3).astype(np.float32)
+    w.update({"mm_projector.0.weight": f(DRIVER_D, 24), "mm_projector.0.bias": f(DRIVER_D),
+              "mm_projector.2.weight": f(DRIVER_D, DRIVER_D) * 0.5, "mm_projector.2.bias": f(DRIVER_D)})
+    return w
+
+
 def driver_frames(w, sig, dino):
     """What cambrian_arch.py:1146-1299 turns the tower features into for square frames:
     mm_projector(cat(siglip, dino)) on the 12x12 grid + one image_newline per grid row -> [n,156,d]."""
     feats = torch.from_numpy(np.concatenate([sig, dino], -1))
-    proj = F.linear(feats, torch.from_numpy(w["mm_projector.weight"]), torch.from_numpy(w["mm_projector.bias"]))
+    if "mm_projector.0.weight" in w:
+        tt = lambda k: torch.from_numpy(w[k])
+        proj = F.linear(F.gelu(F.linear(feats, tt("mm_projector.0.weight"), tt("mm_projector.0.bias"))),
+                        tt("mm_projector.2.weight"), tt("mm_projector.2.bias"))
+    else:
+        proj = F.linear(feats, torch.from_numpy(w["mm_projector.weight"]), torch.from_numpy(w["mm_projector.bias"]))
     n = proj.shape[0]
     proj = proj.view(n, 12, 12, -1)
     nl = torch.from_numpy(w["image_newline"]).view(1, 1, 1, -1).expand(n, 12, 1, -1)
@@ -163,6 +180,42 @@ def make_driver_goldens(only=None):
                             segment_frame_indices=ref["segment_frame_indices"].numpy().astype(np.int64),
                             visual_tokens=ref["visual_tokens"].numpy().astype(np.float32))
         print(f"driver {name}: tokens {tuple(ref['visual_tokens'].shape)}")
+
+
+# ---- "towers" goldens: the same real driver, with the shipped GELU-MLP projector, for the upstream entry
+# (tdc_compress_frames: tower features in, token sequence out).  name -> as DRIVER_CASES
+TOWER_CASES = {
+    "avgpool_text_audio_29f": (29, 8, "Avg_pool", True, True, 100000, "sparse"),
+    "learned_notext_31f": (31, 8, "learned", False, True, 100000, None),
+    "avgpool_notext_40f": (40, 8, "Avg_pool", False, True, 100000, None),
+}
+
+
+def make_tower_goldens(only=None):
+    from oracle import harness
+    for name, (n, K, qt, text, static, max_len, audio) in TOWER_CASES.items():
+        if only and ("towers_" + name) not in only and name not in only:
+            continue
+        w = driver_weights_mlp(140 + n, K)
+        sig, dino = driver_tables(150 + n, n)
+        akw = {}
+        if audio:
+            windows, flags, seconds, proj = driver_audio(160 + n, n, audio)
+            w.update(proj)
+            akw = dict(audio_windows=windows, video_indices=torch.tensor(flags, dtype=torch.int16), audio_seconds=seconds)
+        ref = harness.run_reference_driver(w, DRIVER_GEOM, n, d_llm=DRIVER_D, context_token_num=K, query_type=qt,
+                                           text_input=text, add_static=static, tokenizer_model_max_length=max_len,
+                                           prompt_ids=[[3, 9, 4, 1]], siglip_table=sig, dino_table=dino, **akw)
+        assert torch.allclose(ref["frames"], driver_frames(w, sig, dino), atol=1e-5)
+        meta = dict(n_frames=n, num_query=K, query_type=qt, text=text, add_static=static,
+                    tokenizer_model_max_length=max_len, max_visual_len=max_len - 16 - 3, prompt_ids=[3, 9, 4, 1],
+                    weight_seed=140 + n, table_seed=150 + n, audio=audio, audio_seed=160 + n, projector="mlp2x_gelu",
+                    generator="oracle/make_golden.py: reference prepare_inputs_labels_for_multimodal via "
+                              "oracle/harness.py with the nn.Sequential(Linear, GELU, Linear) mm_projector")
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"towers_{name}.npz"), meta=json.dumps(meta),
+                            segment_frame_indices=ref["segment_frame_indices"].numpy().astype(np.int64),
+                            visual_tokens=ref["visual_tokens"].numpy().astype(np.float32))
+        print(f"towers {name}: tokens {tuple(ref['visual_tokens'].shape)}")
 
 
 # ---- SVA goldens: reference VisionTokenSampler + mm_projector_aux + real window rearrangement ----------------
@@ -247,6 +300,7 @@ def main(only=None):
                             hidden=hidden.astype(np.float32), compressed=comp.astype(np.float32))
         print(f"{name}: hidden {hidden.shape} compressed {comp.shape}")
     make_driver_goldens(only)
+    make_tower_goldens(only)
     make_sva_goldens(only)
 
 

@@ -17,13 +17,14 @@ TDC_OK = 0
 STATUS_NAMES = {0: "TDC_OK", -1: "TDC_EINVAL", -2: "TDC_ECUDA", -3: "TDC_ENOMEM", -4: "TDC_ESTATE",
                 -5: "TDC_EWORKSPACE"}
 TDC_BF16, TDC_F16, TDC_F32 = 0, 1, 2
-K_KV_GEMM, K_QUERY_GEMM, K_ATTENTION, K_ROWOPS, K_COUNT = 0, 1, 2, 3, 4
-KERNEL_CLASS_NAMES = ["kv_gemm", "query_gemm", "attention", "rowops"]
+K_KV_GEMM, K_QUERY_GEMM, K_ATTENTION, K_ROWOPS, K_FRONTEND, K_COUNT = 0, 1, 2, 3, 4, 5
+KERNEL_CLASS_NAMES = ["kv_gemm", "query_gemm", "attention", "rowops", "frontend"]
 
 # every symbol include/tdc_b200.h declares (checked by tests/test_c_abi.py)
 EXPORTED_SYMBOLS = [
     "tdc_abi_version", "tdc_create", "tdc_destroy", "tdc_last_error", "tdc_load_weights", "tdc_workspace_bytes",
-    "tdc_qformer_forward", "tdc_proj_norm", "tdc_compress", "tdc_compress_multicast", "tdc_linear", "tdc_gelu_mlp", "tdc_avg_pool_tokens",
+    "tdc_qformer_forward", "tdc_proj_norm", "tdc_compress", "tdc_compress_multicast", "tdc_frames_workspace_bytes",
+    "tdc_compress_frames", "tdc_linear", "tdc_gelu_mlp", "tdc_avg_pool_tokens",
     "tdc_convert", "tdc_layernorm", "tdc_attention", "tdc_residual_add", "tdc_segment_workspace_bytes", "tdc_segment_boundaries", "tdc_set_profiling", "tdc_get_profile", "tdc_reset_profile", "tdc_launch_count",
 ]
 
@@ -32,13 +33,26 @@ class TdcConfig(C.Structure):
     _fields_ = [
         ("hidden", C.c_int32), ("heads", C.c_int32), ("intermediate", C.c_int32), ("layers", C.c_int32),
         ("cross_freq", C.c_int32), ("d_enc", C.c_int32), ("d_out", C.c_int32), ("vocab", C.c_int32),
-        ("max_pos", C.c_int32), ("ln_eps", C.c_float), ("gemm_cta_group", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("max_pos", C.c_int32), ("ln_eps", C.c_float), ("gemm_cta_group", C.c_int32), ("d_frame_in", C.c_int32),
+        ("d_audio", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
 class TdcTensor(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("dtype", C.c_int32), ("ndim", C.c_int32),
                 ("shape", C.c_int64 * 4)]
+
+
+class TdcFramesArgs(C.Structure):
+    """tdc_frames_args (include/tdc_b200.h)."""
+    _fields_ = [
+        ("frames", C.c_void_p), ("audio", C.c_void_p), ("static_frames", C.c_void_p), ("row_frames", C.c_void_p),
+        ("row_chunk", C.c_void_p), ("input_ids", C.c_void_p),
+        ("n_frames", C.c_int32), ("n_chunks", C.c_int32), ("rows", C.c_int32), ("visual_tokens", C.c_int32),
+        ("audio_tokens", C.c_int32), ("num_query", C.c_int32), ("num_text", C.c_int32),
+        ("learned_queries", C.c_int32), ("fold", C.c_int32), ("multicast", C.c_int32), ("out_dtype", C.c_int32),
+        ("static_out", C.c_void_p), ("out", C.c_void_p),
+    ]
 
 
 _lib: Optional[C.CDLL] = None
@@ -59,6 +73,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.tdc_compress.argtypes = fwd
     lib.tdc_compress_multicast.argtypes = fwd
     lib.tdc_compress_multicast.restype = C.c_int
+    lib.tdc_frames_workspace_bytes.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32]
+    lib.tdc_frames_workspace_bytes.restype = sz
+    lib.tdc_compress_frames.argtypes = [vp, C.POINTER(TdcFramesArgs), vp, sz, vp]
+    lib.tdc_compress_frames.restype = C.c_int
     lib.tdc_proj_norm.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp, sz, vp]
     lib.tdc_linear.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.tdc_gelu_mlp.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
@@ -96,7 +114,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         build_library()
     lib = C.CDLL(str(LIB_PATH))
     _declare(lib)
-    if lib.tdc_abi_version() != 1:
+    if lib.tdc_abi_version() != 2:
         raise RuntimeError("libtdc_b200.so ABI version mismatch; rebuild with `python -m tdc_video_b200.build --force`")
     _lib = lib
     return lib

@@ -108,7 +108,8 @@ class TDCCompressor(nn.Module):
 
     def __init__(self, llm_hidden_size: int, context_token_num: int = 16, query_type: str = "Avg_pool",
                  text_input: bool = True, add_static: bool = True, audio_input: bool = False,
-                 qformer_config: Optional[QFormerConfig] = None, with_lm_head: bool = False):
+                 qformer_config: Optional[QFormerConfig] = None, with_lm_head: bool = False,
+                 mm_input_size: int = 0):
         super().__init__()
         if query_type not in ("Avg_pool", "learned"):
             raise ValueError("query_type must be 'Avg_pool' or 'learned' (cambrian_arch.py:1633-1640)")
@@ -128,13 +129,76 @@ class TDCCompressor(nn.Module):
         self.frame_seg = nn.Parameter(torch.randn(llm_hidden_size))
         if audio_input:
             self.audio_proj = nn.Linear(768, llm_hidden_size)
+        if mm_input_size:
+            # the upstream entry also owns the projector and the newline vector, under the reference's names
+            # (cambrian_arch.py:65-69 `mm_projector`, :148 `image_newline`)
+            from .projector import GeluMLPProjector
+            self.mm_projector = GeluMLPProjector(mm_input_size, llm_hidden_size)
+            self.image_newline = nn.Parameter(torch.randn(llm_hidden_size) * (1.0 / math.sqrt(llm_hidden_size)))
+        self.mm_input_size = mm_input_size
         self.eval()
 
     # ------------------------------------------------------------------------------------
     def _engine(self):
+        if self.mm_input_size:
+            return self._frames_engine()   # a superset handle: no rebuild when both entries are used
         extra = {"vision_proj.weight": self.vision_proj.weight, "vision_proj.bias": self.vision_proj.bias}
         key = (self.vision_proj.weight.data_ptr(), self.vision_proj.weight._version, self.vision_proj.bias._version)
         return self.Qformer.bert.engine(d_out=self.llm_hidden_size, extra_state=extra, extra_key=key)
+
+    def _frames_engine(self):
+        """One handle with everything the upstream entry needs (tdc_compress_frames)."""
+        if not self.mm_input_size:
+            raise RuntimeError("TDCCompressor was built without mm_input_size: no mm_projector / image_newline")
+        l0, l2 = getattr(self.mm_projector, "0"), getattr(self.mm_projector, "2")
+        extra = {"vision_proj.weight": self.vision_proj.weight, "vision_proj.bias": self.vision_proj.bias,
+                 "mm_projector.0.weight": l0.weight, "mm_projector.0.bias": l0.bias,
+                 "mm_projector.2.weight": l2.weight, "mm_projector.2.bias": l2.bias,
+                 "image_newline": self.image_newline, "query_proj.weight": self.query_proj.weight,
+                 "query_proj.bias": self.query_proj.bias, "query_tokens": self.query_tokens}
+        d_audio = 0
+        if hasattr(self, "audio_proj"):
+            extra.update({"audio_proj.weight": self.audio_proj.weight, "audio_proj.bias": self.audio_proj.bias})
+            d_audio = self.audio_proj.in_features
+        key = ("frames",) + tuple((t.data_ptr(), t._version) for t in extra.values())
+        return self.Qformer.bert.engine(d_out=self.llm_hidden_size, extra_state=extra, extra_key=key,
+                                        d_frame_in=self.mm_input_size, d_audio=d_audio)
+
+    @torch.no_grad()
+    def compress_video_from_towers(self, tower_features: torch.Tensor, segment_sizes: Sequence[int],
+                                   input_ids: Optional[torch.Tensor] = None,
+                                   audio_frames: Optional[torch.Tensor] = None,
+                                   max_visual_len: Optional[int] = None, fold: bool = True):
+        """`compress_video` from the towers' outputs: tower_features [n_frames, Tv, mm_input_size] is what the
+        reference feeds to `mm_projector` (cambrian_arch.py:1149).  The projector, the newline tokens, audio_proj,
+        the query build and the Q-Former all run inside ONE library call (tdc_compress_frames); with `fold` the
+        dynamic frames never materialise their d_llm-wide tokens.  Returns the same token sequence as
+        `compress_video(append_newline(mm_projector(tower_features)), ...)`."""
+        if self.training:
+            raise RuntimeError("TDCCompressor is inference-only (eval mode)")
+        if not tower_features.is_cuda:
+            raise RuntimeError("TDCCompressor needs CUDA tensors: there is no CPU fallback")
+        if not self.add_static:
+            raise NotImplementedError("compress_video_from_towers keeps the key frames (add_static=True)")
+        n_frames, Tv, _ = tower_features.shape
+        if sum(int(s) for s in segment_sizes) != n_frames:
+            raise ValueError("segment_sizes must sum to the number of frames")
+        dev = tower_features.device
+        dtype = tower_features.dtype if tower_features.dtype in (torch.bfloat16, torch.float16) else torch.float32
+        plan = plan_chunks(segment_sizes, True)
+        ids = None
+        if self.text_input and input_ids is not None and input_ids.numel() > 0:
+            ids = input_ids.reshape(1, -1)
+        if audio_frames is not None and not hasattr(self, "audio_proj"):
+            raise RuntimeError("audio_frames given but the compressor was built with audio_input=False")
+        static_tok, comp = self._frames_engine().compress_frames(
+            tower_features, torch.from_numpy(plan.static_frames.astype(np.int32)),
+            torch.from_numpy(plan.row_frames.astype(np.int32)), torch.from_numpy(plan.row_chunk.astype(np.int32)),
+            audio=audio_frames, input_ids=ids, num_query=self.context_token_num,
+            learned_queries=self.query_type == "learned", fold=fold, want_static=True, out_dtype=dtype)
+        prep = dict(plan=plan, static_tok=static_tok, L=static_tok.shape[1], d=self.llm_hidden_size, dev=dev,
+                    dtype=dtype)
+        return self._assemble(prep, comp, max_visual_len)
 
     def build_queries(self, static_visual: torch.Tensor):
         """[C, Lv, d] visual-only key frames -> query sets [C, K, hidden] fp32 (cambrian_arch.py:1629-1640).

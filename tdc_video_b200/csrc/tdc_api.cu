@@ -61,7 +61,21 @@ struct tdc_handle {
   __nv_bfloat16* w_ckv = nullptr; float* b_ckv = nullptr;  // [n_cross*2H, d_enc]
   float* word_emb = nullptr; float* pos_emb = nullptr; float* ln_e_g = nullptr; float* ln_e_b = nullptr;
   __nv_bfloat16* w_vp = nullptr; float* b_vp = nullptr;
+  // upstream ("frames") entry: mm_projector, image_newline, query_proj, audio_proj and the folded K/V weights
+  __nv_bfloat16* w_p0 = nullptr; float* b_p0 = nullptr;      // mm_projector.0 [d, d_in]
+  __nv_bfloat16* w_p2 = nullptr; float* b_p2 = nullptr;      // mm_projector.2 [d, d]
+  __nv_bfloat16* w_p2t = nullptr;                            // its transpose (fold scratch)
+  float* newline = nullptr;                                  // image_newline [d]
+  __nv_bfloat16* w_qp = nullptr; float* b_qp = nullptr;      // query_proj [hidden, d]
+  float* query_tokens = nullptr;                             // learned queries [K_max, hidden] (optional)
+  int query_tokens_rows = 0;
+  __nv_bfloat16* w_kvf = nullptr; float* b_kvf = nullptr;    // Wckv . W2 [kvw, d], Wckv b2 + b_ckv
+  float* kv_newline = nullptr;                               // Wckv newline + b_ckv [kvw]
+  __nv_bfloat16* w_ap = nullptr; float* b_ap = nullptr;      // audio_proj [d, d_audio]
+  __nv_bfloat16* w_apt = nullptr;                            // transpose (fold scratch)
+  __nv_bfloat16* w_kva = nullptr; float* b_kva = nullptr;    // Wckv . Wap [kvw, d_audio], Wckv b_ap + b_ckv
   bool loaded = false, have_text_ffn = false, have_embeddings = false, have_vp = false;
+  bool have_frontend = false, have_audio = false, have_query_tokens = false;
   std::vector<uint8_t> seen;  // per expected tensor
   std::string last_error;
   bool profiling = false;
@@ -72,6 +86,7 @@ struct tdc_handle {
 namespace {
 
 constexpr size_t kAlign = 256;
+constexpr int kMaxLearnedQueries = 256;  // rows reserved for `query_tokens` (context_token_num <= 256)
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
 int fail(tdc_handle* h, int code, const std::string& msg) {
@@ -105,6 +120,22 @@ void carve_weights(tdc_handle* h, uint8_t* base, size_t* total) {
   if (c.d_out > 0) {
     h->w_vp = cv.take<__nv_bfloat16>(static_cast<size_t>(c.d_out) * H);
     h->b_vp = cv.take<float>(c.d_out);
+  }
+  if (c.d_frame_in > 0) {
+    const size_t D = c.d_enc, kvw = static_cast<size_t>(h->n_cross) * 2 * H;
+    h->w_p0 = cv.take<__nv_bfloat16>(D * c.d_frame_in); h->b_p0 = cv.take<float>(D);
+    h->w_p2 = cv.take<__nv_bfloat16>(D * D); h->b_p2 = cv.take<float>(D);
+    h->w_p2t = cv.take<__nv_bfloat16>(D * D);
+    h->newline = cv.take<float>(D);
+    h->w_qp = cv.take<__nv_bfloat16>(H * D); h->b_qp = cv.take<float>(H);
+    h->query_tokens = cv.take<float>(static_cast<size_t>(kMaxLearnedQueries) * H);
+    h->w_kvf = cv.take<__nv_bfloat16>(kvw * D); h->b_kvf = cv.take<float>(kvw);
+    h->kv_newline = cv.take<float>(kvw);
+    if (c.d_audio > 0) {
+      h->w_ap = cv.take<__nv_bfloat16>(D * c.d_audio); h->b_ap = cv.take<float>(D);
+      h->w_apt = cv.take<__nv_bfloat16>(D * c.d_audio);
+      h->w_kva = cv.take<__nv_bfloat16>(kvw * c.d_audio); h->b_kva = cv.take<float>(kvw);
+    }
   }
   int cross = 0;
   for (int l = 0; l < c.layers; ++l) {
@@ -145,6 +176,21 @@ bool resolve_slot(tdc_handle* h, const std::string& name, Slot* s) {
   auto V = [&](float* p, int64_t r, int grp = 0) { *s = Slot{p, false, r, 0, grp}; return p != nullptr; };
   if (name == "vision_proj.weight") return W(h->w_vp, c.d_out, H, 3);
   if (name == "vision_proj.bias") return V(h->b_vp, c.d_out, 3);
+  if (c.d_frame_in > 0) {
+    const int64_t D = c.d_enc;
+    if (name == "mm_projector.0.weight") return W(h->w_p0, D, c.d_frame_in, 4);
+    if (name == "mm_projector.0.bias") return V(h->b_p0, D, 4);
+    if (name == "mm_projector.2.weight") return W(h->w_p2, D, D, 4);
+    if (name == "mm_projector.2.bias") return V(h->b_p2, D, 4);
+    if (name == "image_newline") return V(h->newline, D, 4);
+    if (name == "query_proj.weight") return W(h->w_qp, H, D, 4);
+    if (name == "query_proj.bias") return V(h->b_qp, H, 4);
+    if (name == "query_tokens") { *s = Slot{h->query_tokens, false, -1, H, 6}; return true; }  // [K, hidden], K free
+    if (c.d_audio > 0) {
+      if (name == "audio_proj.weight") return W(h->w_ap, D, c.d_audio, 5);
+      if (name == "audio_proj.bias") return V(h->b_ap, D, 5);
+    }
+  }
   if (name == "embeddings.LayerNorm.weight") return V(h->ln_e_g, H);
   if (name == "embeddings.LayerNorm.bias") return V(h->ln_e_b, H);
   if (name == "embeddings.word_embeddings.weight") { *s = Slot{h->word_emb, false, c.vocab, H, 2}; return h->word_emb != nullptr; }
@@ -207,6 +253,9 @@ std::vector<std::string> expected_names(const tdc_handle* h, int group) {
   if (group == 0) wb("embeddings.LayerNorm");
   if (group == 2) { out.push_back("embeddings.word_embeddings.weight"); out.push_back("embeddings.position_embeddings.weight"); }
   if (group == 3) wb("vision_proj");
+  if (group == 4) { wb("mm_projector.0"); wb("mm_projector.2"); wb("query_proj"); out.push_back("image_newline"); }
+  if (group == 5) wb("audio_proj");
+  if (group >= 4) return out;
   for (int l = 0; l < c.layers; ++l) {
     const std::string p = "encoder.layer." + std::to_string(l) + ".";
     if (group == 0) {
@@ -309,38 +358,26 @@ int gemm(tdc_handle* h, int cls, cudaStream_t s, const void* a, long long lda, c
   return gemm_launch(p, s, err);
 }
 
-// One batch of rows [row0, row0 + rows) of the call; all pointers in `f` are for the whole call.
-int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long rows, uint8_t* ws_base,
-                  cudaStream_t s) {
+// Where the cross-attention K/V of a row batch live: one dense [slab_rows, 2H] (K | V) matrix per cross layer
+// (`slab_stride` elements apart, row pitch `pitch`).  Row r's KV tokens: seg1 tokens at slab row r*seg1 + t, then
+// seg2 tokens at base2 + r*seg2 + t, then seg3 tokens at base3 + t shared by ALL rows (the image_newline tokens).
+struct KvView {
+  const __nv_bfloat16* base = nullptr;
+  long long slab_stride = 0, pitch = 0;
+  bool slabs = true;   // false: interleaved [rows*L, kvw] layout (odd head counts), seg2 = seg3 = 0
+  int seg1 = 0, seg2 = 0, seg3 = 0;
+  long long base2 = 0, base3 = 0;
+};
+
+// Embeddings + the 12-layer stack + output stage for rows [row0, row0 + rows) whose cross-attention K/V are in `kv`.
+int qformer_layers(tdc_handle* h, const ForwardCall& f, long long row0, long long rows, const Workspace& w,
+                   const KvView& kv, const int* kv_len, cudaStream_t s) {
   const tdc_config& c = h->cfg;
-  const int H = c.hidden, I = c.intermediate, K = f.K, T = f.T, L = f.L, n = K + T;
+  const int H = c.hidden, I = c.intermediate, K = f.K, T = f.T, n = K + T;
   const char* err = nullptr;
-  const bool enc_convert = f.enc_dtype != TDC_BF16;
-  Workspace w = carve_workspace(h, ws_base, rows, L, K, T, enc_convert, f.compress);
-  const size_t esz = f.enc_dtype == TDC_F32 ? 4 : 2;
-  const uint8_t* enc_in = static_cast<const uint8_t*>(f.enc) + static_cast<size_t>(row0) * L * c.d_enc * esz;
-  const __nv_bfloat16* enc = reinterpret_cast<const __nv_bfloat16*>(enc_in);
-  if (enc_convert) {
-    KernelScope ks(h, TDC_K_ROWOPS, s);
-    TDC_TRY(convert_launch(enc_in, f.enc_dtype, w.enc_bf16, TDC_BF16, rows * L * c.d_enc, s, &err));
-    enc = w.enc_bf16;
-  }
-  const int* kv_len = f.kv_len ? f.kv_len + row0 : nullptr;
-  const int kvw = 2 * H * h->n_cross;  // K/V columns per KV token over all cross layers
   const float scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
 
-  // 1. every cross layer's K and V for every KV token of every row: the dominant GEMM.  Output layout:
-  //    one dense [rows*L, 2H] (K | V) matrix per cross layer, so that a layer's attention launch streams a
-  //    contiguous region (633 KB per row) instead of 3 KB pieces at an 18 KB stride.  2H is a multiple of
-  //    128 whenever heads is even; odd head counts fall back to the interleaved [rows*L, kvw] layout.
-  const bool kv_slabs = ((2 * H) % 128) == 0;
-  const long long kv_slab_stride = kv_slabs ? rows * L * 2ll * H : 0;
-  const long long kv_pitch = kv_slabs ? 2 * H : kvw;
-  if (h->n_cross > 0)
-    TDC_TRY(gemm(h, TDC_K_KV_GEMM, s, enc, c.d_enc, h->w_ckv, c.d_enc, h->b_ckv, w.kv, kv_pitch, rows * L, kvw,
-                 c.d_enc, EPI_BIAS_BF16, &err, kv_slabs ? 2 * H : 0, kv_slab_stride));
-
-  // 2. embeddings + LayerNorm into the [query slab | text slab] layout
+  // embeddings + LayerNorm into the [query slab | text slab] layout
   {
     EmbedArgs e;
     const size_t qsz = f.query_dtype == TDC_F32 ? 4 : 2;
@@ -396,13 +433,14 @@ int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long
       TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16, H, lw.w_cq, H, lw.b_cq, w.qc, H, MQ, H, H, EPI_BIAS_BF16, &err));
       AttentionArgs a;
       a.q = w.qc; a.out = w.ctx; a.ldq = H; a.ldo = H;
-      a.k = kv_slabs ? w.kv + static_cast<size_t>(lw.cross_index) * kv_slab_stride
-                     : w.kv + static_cast<size_t>(lw.cross_index) * 2 * H;
+      a.k = kv.slabs ? kv.base + static_cast<size_t>(lw.cross_index) * kv.slab_stride
+                     : kv.base + static_cast<size_t>(lw.cross_index) * 2 * H;
       a.v = a.k + H;
-      a.ldk = a.ldv = kv_pitch;
+      a.ldk = a.ldv = kv.pitch;
       a.rows = static_cast<int>(rows); a.heads = c.heads; a.nq = K;
       a.q_seg1 = K; a.q_seg2 = 0;
-      a.kv_seg1 = L; a.kv_seg2 = 0;
+      a.kv_seg1 = kv.seg1; a.kv_seg2 = kv.seg2; a.kv_seg3 = kv.seg3;
+      a.kv_base2 = kv.base2; a.kv_base3 = kv.base3;
       a.kv_len = kv_len;
       a.scale_log2 = scale_log2;
       {
@@ -442,6 +480,225 @@ int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long
     TDC_TRY(l2_normalize_launch(w.proj, c.d_out, out, f.out_dtype, MQ, c.d_out, f.multicast, s, &err));
   }
   return TDC_OK;
+}
+
+// One batch of rows [row0, row0 + rows) of the call; all pointers in `f` are for the whole call.
+int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long rows, uint8_t* ws_base,
+                  cudaStream_t s) {
+  const tdc_config& c = h->cfg;
+  const int H = c.hidden, K = f.K, T = f.T, L = f.L;
+  const char* err = nullptr;
+  const bool enc_convert = f.enc_dtype != TDC_BF16;
+  Workspace w = carve_workspace(h, ws_base, rows, L, K, T, enc_convert, f.compress);
+  const size_t esz = f.enc_dtype == TDC_F32 ? 4 : 2;
+  const uint8_t* enc_in = static_cast<const uint8_t*>(f.enc) + static_cast<size_t>(row0) * L * c.d_enc * esz;
+  const __nv_bfloat16* enc = reinterpret_cast<const __nv_bfloat16*>(enc_in);
+  if (enc_convert) {
+    KernelScope ks(h, TDC_K_ROWOPS, s);
+    TDC_TRY(convert_launch(enc_in, f.enc_dtype, w.enc_bf16, TDC_BF16, rows * L * c.d_enc, s, &err));
+    enc = w.enc_bf16;
+  }
+  const int kvw = 2 * H * h->n_cross;  // K/V columns per KV token over all cross layers
+
+  // every cross layer's K and V for every KV token of every row: the dominant GEMM.  Output layout:
+  // one dense [rows*L, 2H] (K | V) matrix per cross layer, so that a layer's attention launch streams a
+  // contiguous region (633 KB per row) instead of 3 KB pieces at an 18 KB stride.  2H is a multiple of
+  // 128 whenever heads is even; odd head counts fall back to the interleaved [rows*L, kvw] layout.
+  KvView kv;
+  kv.base = w.kv;
+  kv.slabs = ((2 * H) % 128) == 0;
+  kv.slab_stride = kv.slabs ? rows * L * 2ll * H : 0;
+  kv.pitch = kv.slabs ? 2 * H : kvw;
+  kv.seg1 = L;
+  if (h->n_cross > 0)
+    TDC_TRY(gemm(h, TDC_K_KV_GEMM, s, enc, c.d_enc, h->w_ckv, c.d_enc, h->b_ckv, w.kv, kv.pitch, rows * L, kvw,
+                 c.d_enc, EPI_BIAS_BF16, &err, kv.slabs ? 2 * H : 0, kv.slab_stride));
+  return qformer_layers(h, f, row0, rows, w, kv, f.kv_len ? f.kv_len + row0 : nullptr, s);
+}
+
+// ---- upstream ("frames") entry -----------------------------------------------------------------------------
+// Weight folding at load time (exact algebra, one extra bf16 rounding of the folded matrices):
+//   K/V of a visual token  = (gelu(x W0^T + b0) W2^T + b2) Wckv^T + b_ckv = gelu(..) (Wckv W2)^T + (Wckv b2 + b_ckv)
+//   K/V of an audio token  = (a Wap^T + b_ap) Wckv^T + b_ckv            = a (Wckv Wap)^T + (Wckv b_ap + b_ckv)
+//   K/V of a newline token = Wckv newline + b_ckv                         (the same for every frame)
+// so that a dynamic frame never materialises its d_llm-wide tokens: mm_projector.2 and audio_proj only run on the
+// key frames (which pass through to the LLM, cambrian_arch.py:1617-1623).
+int fold_frontend_weights(tdc_handle* h, cudaStream_t s) {
+  const tdc_config& c = h->cfg;
+  const int D = c.d_enc, kvw = 2 * c.hidden * h->n_cross;
+  const char* err = nullptr;
+  auto fold = [&](const __nv_bfloat16* w_t, int n, __nv_bfloat16* out) -> int {  // out[kvw, n] = Wckv . w_t[n, D]^T
+    GemmProblem p;
+    p.a = h->w_ckv; p.lda = D; p.w = w_t; p.ldw = D; p.bias = nullptr; p.out = out; p.ldo = n;
+    p.m = kvw; p.n = n; p.k = D; p.mode = EPI_BIAS_BF16; p.cta_group = 2;
+    ++h->launches;
+    return gemm_launch(p, s, &err);
+  };
+  if (h->n_cross > 0) {
+    TDC_TRY(transpose_bf16_launch(h->w_p2, D, D, h->w_p2t, s, &err));
+    TDC_TRY(fold(h->w_p2t, D, h->w_kvf));
+    TDC_TRY(matvec_bias_launch(h->w_ckv, h->b_p2, h->b_ckv, h->b_kvf, kvw, D, s, &err));
+    TDC_TRY(matvec_bias_launch(h->w_ckv, h->newline, h->b_ckv, h->kv_newline, kvw, D, s, &err));
+    h->launches += 3;
+    if (h->have_audio) {
+      TDC_TRY(transpose_bf16_launch(h->w_ap, D, c.d_audio, h->w_apt, s, &err));
+      TDC_TRY(fold(h->w_apt, c.d_audio, h->w_kva));
+      TDC_TRY(matvec_bias_launch(h->w_ckv, h->b_ap, h->b_ckv, h->b_kva, kvw, D, s, &err));
+      h->launches += 2;
+    }
+  }
+  return TDC_OK;
+}
+
+struct FramesCall {
+  const tdc_frames_args* a;
+  int side;        // token grid side: Tv = side * side
+  int Tv, Ta, K, T;
+  bool learned;    // queries = the loaded query_tokens instead of avg-pool(key frame) -> query_proj
+};
+
+struct FramesWorkspace {
+  // whole call
+  float* q_sets;       // [n_chunks, K, H] fp32 (Avg_pool queries, one set per chunk)
+  int32_t* zero_map;   // [rows] zeros: "every row uses set 0" (shared prompt / learned queries)
+  // per batch of nb items (nb key frames in the static pass, nb rows in the dynamic pass)
+  __nv_bfloat16* fin;     // [nb*Tv, d_in]   gathered tower features
+  __nv_bfloat16* pmid;    // [nb*Tv, d]      gelu(mm_projector.0)
+  __nv_bfloat16* xv;      // [nb*Tv, d]      projected visual tokens (key frames; dynamic frames only if !fold)
+  __nv_bfloat16* ain;     // [nb*Ta, d_audio]
+  __nv_bfloat16* xa;      // [nb*Ta, d]
+  __nv_bfloat16* pooled;  // [nb*K, d]
+  __nv_bfloat16* kv;      // n_cross slabs of [nb*(Tv+Ta) + side, 2H]
+  uint8_t* qws;           // Q-Former workspace of nb rows (carve_workspace without the kv / enc parts)
+  size_t bytes;
+};
+
+FramesWorkspace carve_frames(const tdc_handle* h, uint8_t* base, long long n_chunks, long long rows, long long nb,
+                             int Tv, int Ta, int side, int K, int T) {
+  const tdc_config& c = h->cfg;
+  const size_t D = c.d_enc, H = c.hidden, N = static_cast<size_t>(nb);
+  Carver cv{base};
+  FramesWorkspace w{};
+  w.q_sets = cv.take<float>(static_cast<size_t>(n_chunks) * K * H);
+  w.zero_map = cv.take<int32_t>(static_cast<size_t>(rows));
+  w.fin = cv.take<__nv_bfloat16>(N * Tv * c.d_frame_in);
+  w.pmid = cv.take<__nv_bfloat16>(N * Tv * D);
+  w.xv = cv.take<__nv_bfloat16>(N * Tv * D);
+  w.ain = cv.take<__nv_bfloat16>(N * Ta * std::max(c.d_audio, 8));
+  w.xa = cv.take<__nv_bfloat16>(N * Ta * D);
+  w.pooled = cv.take<__nv_bfloat16>(N * K * D);
+  w.kv = cv.take<__nv_bfloat16>((N * (Tv + Ta) + side) * 2 * H * h->n_cross);
+  w.qws = base ? base + cv.off : nullptr;
+  // the Q-Former's own buffers: carve_workspace with L = 0 drops its enc / kv parts
+  cv.off += carve_workspace(h, nullptr, nb, 0, K, T, false, true).bytes;
+  w.bytes = cv.off;
+  return w;
+}
+
+int frames_gemm(tdc_handle* h, int cls, cudaStream_t s, const void* a, long long k, const void* w, const float* bias,
+                void* out, long long m, int n, int mode, const char** err, int slab_cols = 0, long long slab_stride = 0,
+                long long ldo = 0) {
+  return gemm(h, cls, s, a, k, w, k, bias, out, ldo > 0 ? ldo : n, m, n, static_cast<int>(k), mode, err, slab_cols,
+              slab_stride);
+}
+
+// Key frames [c0, c0 + cb): mm_projector -> (pool -> query_proj -> q_sets) and (assemble static_out).
+int frames_static_batch(tdc_handle* h, const FramesCall& fc, const FramesWorkspace& w, long long c0, long long cb,
+                        cudaStream_t s) {
+  const tdc_config& c = h->cfg;
+  const tdc_frames_args& a = *fc.a;
+  const int D = c.d_enc, H = c.hidden, Tv = fc.Tv, Ta = fc.Ta, K = fc.K;
+  const char* err = nullptr;
+  {
+    KernelScope ks(h, TDC_K_FRONTEND, s);
+    TDC_TRY(gather_blocks_launch(a.frames, a.static_frames + c0, w.fin, cb, static_cast<long long>(Tv) * c.d_frame_in * 2,
+                                 s, &err));
+  }
+  TDC_TRY(frames_gemm(h, TDC_K_FRONTEND, s, w.fin, c.d_frame_in, h->w_p0, h->b_p0, w.pmid, cb * Tv, D,
+                      EPI_BIAS_GELU_BF16, &err));
+  TDC_TRY(frames_gemm(h, TDC_K_FRONTEND, s, w.pmid, D, h->w_p2, h->b_p2, w.xv, cb * Tv, D, EPI_BIAS_BF16, &err));
+  if (!fc.learned) {
+    {
+      KernelScope ks(h, TDC_K_FRONTEND, s);
+      TDC_TRY(pool_static_queries_launch(w.xv, h->newline, static_cast<int>(cb), fc.side, D, K, w.pooled, s, &err));
+    }
+    TDC_TRY(frames_gemm(h, TDC_K_FRONTEND, s, w.pooled, D, h->w_qp, h->b_qp, w.q_sets + c0 * K * H, cb * K, H,
+                        EPI_BIAS_F32, &err));
+  }
+  if (a.static_out != nullptr) {
+    if (Ta > 0) {
+      {
+        KernelScope ks(h, TDC_K_FRONTEND, s);
+        TDC_TRY(gather_blocks_launch(a.audio, a.static_frames + c0, w.ain, cb, static_cast<long long>(Ta) * c.d_audio * 2,
+                                     s, &err));
+      }
+      TDC_TRY(frames_gemm(h, TDC_K_FRONTEND, s, w.ain, c.d_audio, h->w_ap, h->b_ap, w.xa, cb * Ta, D, EPI_BIAS_BF16,
+                          &err));
+    }
+    const size_t osz = a.out_dtype == TDC_F32 ? 4 : 2;
+    const long long ls = static_cast<long long>(fc.side) * (fc.side + 1) + Ta;
+    KernelScope ks(h, TDC_K_FRONTEND, s);
+    TDC_TRY(assemble_static_launch(w.xv, w.xa, h->newline, static_cast<int>(cb), fc.side, Ta, D,
+                                   static_cast<uint8_t*>(a.static_out) + static_cast<size_t>(c0) * ls * D * osz,
+                                   a.out_dtype, s, &err));
+  }
+  return TDC_OK;
+}
+
+// Dynamic frames (rows) [r0, r0 + rb): mm_projector.0 -> K/V of the frame's visual, audio and newline tokens ->
+// Q-Former + vision_proj + L2-normalise.
+int frames_dynamic_batch(tdc_handle* h, const FramesCall& fc, const ForwardCall& f, const FramesWorkspace& w,
+                         long long r0, long long rb, cudaStream_t s) {
+  const tdc_config& c = h->cfg;
+  const tdc_frames_args& a = *fc.a;
+  const int D = c.d_enc, H = c.hidden, Tv = fc.Tv, Ta = fc.Ta;
+  const int kvw = 2 * H * h->n_cross;
+  const char* err = nullptr;
+  KvView kv;
+  kv.base = w.kv;
+  kv.pitch = 2 * H;
+  kv.seg1 = Tv; kv.seg2 = Ta; kv.seg3 = fc.side;
+  kv.base2 = rb * Tv;
+  kv.base3 = rb * (Tv + Ta);
+  kv.slab_stride = (rb * (Tv + Ta) + fc.side) * 2ll * H;
+  {
+    KernelScope ks(h, TDC_K_FRONTEND, s);
+    TDC_TRY(gather_blocks_launch(a.frames, a.row_frames + r0, w.fin, rb, static_cast<long long>(Tv) * c.d_frame_in * 2,
+                                 s, &err));
+  }
+  TDC_TRY(frames_gemm(h, TDC_K_FRONTEND, s, w.fin, c.d_frame_in, h->w_p0, h->b_p0, w.pmid, rb * Tv, D,
+                      EPI_BIAS_GELU_BF16, &err));
+  if (h->n_cross > 0) {
+    if (a.fold) {
+      TDC_TRY(frames_gemm(h, TDC_K_KV_GEMM, s, w.pmid, D, h->w_kvf, h->b_kvf, w.kv, rb * Tv, kvw, EPI_BIAS_BF16, &err,
+                          2 * H, kv.slab_stride, 2 * H));
+    } else {
+      TDC_TRY(frames_gemm(h, TDC_K_FRONTEND, s, w.pmid, D, h->w_p2, h->b_p2, w.xv, rb * Tv, D, EPI_BIAS_BF16, &err));
+      TDC_TRY(frames_gemm(h, TDC_K_KV_GEMM, s, w.xv, D, h->w_ckv, h->b_ckv, w.kv, rb * Tv, kvw, EPI_BIAS_BF16, &err,
+                          2 * H, kv.slab_stride, 2 * H));
+    }
+    if (Ta > 0) {
+      {
+        KernelScope ks(h, TDC_K_FRONTEND, s);
+        TDC_TRY(gather_blocks_launch(a.audio, a.row_frames + r0, w.ain, rb, static_cast<long long>(Ta) * c.d_audio * 2,
+                                     s, &err));
+      }
+      __nv_bfloat16* kv_aud = w.kv + kv.base2 * 2 * H;
+      if (a.fold) {
+        TDC_TRY(frames_gemm(h, TDC_K_KV_GEMM, s, w.ain, c.d_audio, h->w_kva, h->b_kva, kv_aud, rb * Ta, kvw,
+                            EPI_BIAS_BF16, &err, 2 * H, kv.slab_stride, 2 * H));
+      } else {
+        TDC_TRY(frames_gemm(h, TDC_K_FRONTEND, s, w.ain, c.d_audio, h->w_ap, h->b_ap, w.xa, rb * Ta, D, EPI_BIAS_BF16,
+                            &err));
+        TDC_TRY(frames_gemm(h, TDC_K_KV_GEMM, s, w.xa, D, h->w_ckv, h->b_ckv, kv_aud, rb * Ta, kvw, EPI_BIAS_BF16, &err,
+                            2 * H, kv.slab_stride, 2 * H));
+      }
+    }
+    KernelScope ks(h, TDC_K_FRONTEND, s);
+    TDC_TRY(broadcast_rows_launch(h->kv_newline, 2 * H, h->n_cross, w.kv, kv.slab_stride, kv.base3, fc.side, s, &err));
+  }
+  Workspace qw = carve_workspace(h, w.qws, rb, 0, fc.K, fc.T, false, true);
+  return qformer_layers(h, f, r0, rb, qw, kv, nullptr, s);
 }
 
 int validate_call(tdc_handle* h, const ForwardCall& f) {
@@ -506,6 +763,7 @@ int tdc_create(tdc_handle** out, const tdc_config* cfg) {
   if (c.d_enc <= 0 || c.d_enc % 8 || c.d_out < 0 || c.d_out % 8) { g_create_error = "d_enc and d_out must be multiples of 8"; return TDC_EINVAL; }
   if (c.vocab < 0 || (c.vocab > 0 && c.max_pos <= 0)) { g_create_error = "bad vocab / max_pos"; return TDC_EINVAL; }
   if (c.gemm_cta_group < 0 || c.gemm_cta_group > 2) { g_create_error = "gemm_cta_group must be 0, 1 or 2"; return TDC_EINVAL; }
+  if (c.d_frame_in < 0 || c.d_frame_in % 8 || c.d_audio < 0 || c.d_audio % 8) { g_create_error = "d_frame_in and d_audio must be multiples of 8"; return TDC_EINVAL; }
   int dev_count = 0;
   if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) { g_create_error = "no CUDA device: libtdc_b200 has no CPU fallback"; return TDC_ECUDA; }
   int dev = 0, major = 0;
@@ -551,8 +809,14 @@ int tdc_load_weights(tdc_handle* h, const tdc_tensor* tensors, int32_t count, td
     if (!resolve_slot(h, name, &slot)) continue;  // tensors the path does not use (cls.*, position_ids, ...) are ignored
     int64_t numel = 1;
     for (int d = 0; d < t.ndim; ++d) numel *= t.shape[d];
-    const bool shape_ok = slot.cols == 0 ? (t.ndim == 1 && t.shape[0] == slot.rows)
-                                         : (t.ndim == 2 && t.shape[0] == slot.rows && t.shape[1] == slot.cols);
+    bool shape_ok = slot.cols == 0 ? (t.ndim == 1 && t.shape[0] == slot.rows)
+                                   : (t.ndim == 2 && t.shape[0] == slot.rows && t.shape[1] == slot.cols);
+    if (slot.rows == -1) {  // query_tokens [1, K, hidden] or [K, hidden]: K is free (<= kMaxLearnedQueries)
+      const int64_t kq = t.ndim == 3 ? t.shape[1] : t.shape[0];
+      shape_ok = ((t.ndim == 3 && t.shape[0] == 1 && t.shape[2] == slot.cols) || (t.ndim == 2 && t.shape[1] == slot.cols)) &&
+                 kq >= 1 && kq <= kMaxLearnedQueries;
+      if (shape_ok) { h->query_tokens_rows = static_cast<int>(kq); h->have_query_tokens = true; }
+    }
     if (!shape_ok) return fail(h, TDC_EINVAL, "shape mismatch for tensor " + name);
     const char* err = nullptr;
     const int rc = convert_launch(t.data, t.dtype, slot.dst, slot.as_bf16 ? TDC_BF16 : TDC_F32, numel, s, &err);
@@ -571,6 +835,12 @@ int tdc_load_weights(tdc_handle* h, const tdc_tensor* tensors, int32_t count, td
   h->have_text_ffn = h->cfg.vocab > 0 && have_all(1, nullptr);
   h->have_embeddings = h->cfg.vocab > 0 && have_all(2, nullptr);
   h->have_vp = h->cfg.d_out > 0 && have_all(3, nullptr);
+  h->have_frontend = h->cfg.d_frame_in > 0 && h->have_vp && have_all(4, nullptr);
+  h->have_audio = h->have_frontend && h->cfg.d_audio > 0 && have_all(5, nullptr);
+  if (h->have_frontend) {
+    const int rc = fold_frontend_weights(h, s);
+    if (rc != TDC_OK) return rc;
+  }
   h->loaded = true;
   return TDC_OK;
 }
@@ -612,6 +882,96 @@ int tdc_compress_multicast(tdc_handle* h, const void* query_embeds, int32_t quer
                 rows, kv_tokens, num_query, num_text, out_multicast, out_dtype, true};
   f.multicast = true;
   return run_call(h, f, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+size_t tdc_frames_workspace_bytes(const tdc_handle* h, int32_t n_chunks, int32_t rows, int32_t batch,
+                                  int32_t visual_tokens, int32_t audio_tokens, int32_t num_query, int32_t num_text) {
+  if (h == nullptr || n_chunks < 0 || rows < 0 || batch <= 0 || visual_tokens <= 0 || audio_tokens < 0 ||
+      num_query <= 0 || num_text < 0)
+    return 0;
+  int side = 1;
+  while (side * side < visual_tokens) ++side;
+  return carve_frames(h, nullptr, n_chunks, rows, batch, visual_tokens, audio_tokens, side, num_query, num_text).bytes;
+}
+
+int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* workspace, size_t workspace_bytes,
+                        tdc_stream_t stream) {
+  if (h == nullptr) return TDC_EINVAL;
+  if (args == nullptr) return fail(h, TDC_EINVAL, "null tdc_frames_args");
+  const tdc_frames_args& a = *args;
+  const tdc_config& c = h->cfg;
+  if (!h->loaded || !h->have_frontend)
+    return fail(h, TDC_ESTATE, "tdc_compress_frames needs d_frame_in > 0 and the mm_projector / image_newline / "
+                               "query_proj / vision_proj weights");
+  if (c.d_enc != c.d_out) return fail(h, TDC_EINVAL, "tdc_compress_frames needs d_enc == d_out (the LLM width)");
+  if ((2 * c.hidden) % 128 != 0) return fail(h, TDC_EINVAL, "tdc_compress_frames needs an even number of heads");
+  FramesCall fc{};
+  fc.a = args;
+  fc.Tv = a.visual_tokens; fc.Ta = a.audio_tokens; fc.K = a.num_query; fc.T = a.num_text;
+  fc.learned = a.learned_queries != 0;
+  if (a.n_frames < 0 || a.n_chunks < 0 || a.rows < 0 || fc.Tv <= 0 || fc.Ta < 0 || fc.K <= 0 || fc.T < 0)
+    return fail(h, TDC_EINVAL, "bad frame / chunk / row / token counts");
+  fc.side = 1;
+  while (fc.side * fc.side < fc.Tv) ++fc.side;
+  if (fc.side * fc.side != fc.Tv) return fail(h, TDC_EINVAL, "visual_tokens must be a square grid (side * side)");
+  if (fc.Ta > 0 && (!h->have_audio || a.audio == nullptr))
+    return fail(h, TDC_ESTATE, "audio_tokens > 0 needs d_audio > 0, the audio_proj weights and an audio pointer");
+  if (fc.learned && (!h->have_query_tokens || h->query_tokens_rows != fc.K))
+    return fail(h, TDC_ESTATE, "learned_queries needs a loaded `query_tokens` with num_query rows");
+  if (fc.T > 0) {
+    if (a.input_ids == nullptr) return fail(h, TDC_EINVAL, "num_text > 0 needs input_ids");
+    if (!h->have_text_ffn || !h->have_embeddings)
+      return fail(h, TDC_ESTATE, "text input needs the word/position embeddings and the text FFN weights");
+    if (fc.T > c.max_pos) return fail(h, TDC_EINVAL, "num_text exceeds max_position_embeddings");
+  }
+  if (a.out_dtype < TDC_BF16 || a.out_dtype > TDC_F32) return fail(h, TDC_EINVAL, "unknown dtype");
+  if (a.n_chunks == 0 && a.rows == 0) return TDC_OK;
+  if (a.frames == nullptr || (a.n_chunks > 0 && a.static_frames == nullptr) ||
+      (a.rows > 0 && (a.row_frames == nullptr || a.row_chunk == nullptr || a.out == nullptr)))
+    return fail(h, TDC_EINVAL, "null frames / index / out pointer");
+  if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & (kAlign - 1)))
+    return fail(h, TDC_EINVAL, "workspace must be non-null and 256-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+  // internal batch: the largest item count (<= 65535, the gather grid) whose buffers fit the workspace
+  const long long most = std::max<long long>(a.rows, a.n_chunks);
+  long long nb = std::min<long long>(most, 65535);
+  auto need = [&](long long n) { return carve_frames(h, nullptr, a.n_chunks, a.rows, n, fc.Tv, fc.Ta, fc.side, fc.K, fc.T).bytes; };
+  if (need(nb) > workspace_bytes) {
+    const size_t fixed = need(0), one = need(1) - fixed;
+    if (workspace_bytes < fixed + one) return fail(h, TDC_EWORKSPACE, "workspace too small for a single row; see tdc_frames_workspace_bytes");
+    nb = std::min<long long>(nb, static_cast<long long>((workspace_bytes - fixed) / one));
+    while (nb > 0 && need(nb) > workspace_bytes) --nb;
+    if (nb <= 0) return fail(h, TDC_EWORKSPACE, "workspace too small for a single row; see tdc_frames_workspace_bytes");
+  }
+  FramesWorkspace w = carve_frames(h, static_cast<uint8_t*>(workspace), a.n_chunks, a.rows, nb, fc.Tv, fc.Ta, fc.side,
+                                   fc.K, fc.T);
+
+  // pass 1: key frames (queries of every chunk, pass-through tokens)
+  if (a.n_chunks > 0 && (!fc.learned || a.static_out != nullptr))
+    for (long long c0 = 0; c0 < a.n_chunks; c0 += nb) {
+      const int rc = frames_static_batch(h, fc, w, c0, std::min<long long>(nb, a.n_chunks - c0), s);
+      if (rc != TDC_OK) return rc;
+    }
+  if (a.rows == 0) return TDC_OK;
+  // pass 2: dynamic frames
+  const bool zero_map = fc.learned || fc.T > 0;
+  if (zero_map && cudaMemsetAsync(w.zero_map, 0, static_cast<size_t>(a.rows) * sizeof(int32_t), s) != cudaSuccess)
+    return fail(h, TDC_ECUDA, "cudaMemsetAsync failed");
+  ForwardCall f{};
+  f.query_embeds = fc.learned ? h->query_tokens : w.q_sets;
+  f.query_dtype = TDC_F32;
+  f.query_set = fc.learned ? w.zero_map : a.row_chunk;
+  f.input_ids = fc.T > 0 ? a.input_ids : nullptr;
+  f.text_set = fc.T > 0 ? w.zero_map : nullptr;
+  f.enc = nullptr; f.enc_dtype = TDC_BF16; f.kv_len = nullptr;
+  f.rows = a.rows; f.L = fc.Tv + fc.Ta + fc.side; f.K = fc.K; f.T = fc.T;
+  f.out = a.out; f.out_dtype = a.out_dtype; f.compress = true; f.multicast = a.multicast != 0;
+  for (long long r0 = 0; r0 < a.rows; r0 += nb) {
+    const int rc = frames_dynamic_batch(h, fc, f, w, r0, std::min<long long>(nb, a.rows - r0), s);
+    if (rc != TDC_OK) return rc;
+  }
+  return TDC_OK;
 }
 
 int tdc_proj_norm(tdc_handle* h, const void* hidden, int32_t hidden_dtype, int32_t rows, int32_t tokens_per_row,

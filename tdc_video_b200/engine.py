@@ -13,7 +13,7 @@ from typing import Dict, Mapping, Optional
 import torch
 
 from . import _lib
-from ._lib import TdcConfig, TdcTensor, check
+from ._lib import TdcConfig, TdcFramesArgs, TdcTensor, check
 
 _DTYPES = {torch.bfloat16: _lib.TDC_BF16, torch.float16: _lib.TDC_F16, torch.float32: _lib.TDC_F32}
 
@@ -37,17 +37,17 @@ class QFormerEngine:
     """Owns one `tdc_handle` (re-packed bf16 weights on one GPU) and a growable workspace."""
 
     def __init__(self, *, hidden=768, heads=12, intermediate=3072, layers=12, cross_freq=2, d_enc=3584, d_out=0,
-                 vocab=0, max_pos=512, ln_eps=1e-12, device=None, gemm_cta_group=0,
+                 vocab=0, max_pos=512, ln_eps=1e-12, device=None, gemm_cta_group=0, d_frame_in=0, d_audio=0,
                  max_workspace_bytes: int = 8 << 30):
         if not torch.cuda.is_available():
             raise RuntimeError("tdc_video_b200 needs a CUDA (sm_100a) device: there is no CPU fallback")
         self.lib = _lib.load_library()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.cfg = TdcConfig(hidden, heads, intermediate, layers, cross_freq, d_enc, d_out, vocab, max_pos,
-                             float(ln_eps), gemm_cta_group)
+                             float(ln_eps), gemm_cta_group, d_frame_in, d_audio)
         self.geometry = dict(hidden=hidden, heads=heads, intermediate=intermediate, layers=layers,
                              cross_freq=cross_freq, d_enc=d_enc, d_out=d_out, vocab=vocab, max_pos=max_pos,
-                             ln_eps=ln_eps)
+                             ln_eps=ln_eps, d_frame_in=d_frame_in, d_audio=d_audio)
         env_cap = os.environ.get("TDC_MAX_WORKSPACE_GB")   # dev knob: smaller workspace = smaller internal row batches
         self.max_workspace_bytes = int(float(env_cap) * (1 << 30)) if env_cap else int(max_workspace_bytes)
         self._ws: Optional[torch.Tensor] = None
@@ -73,6 +73,8 @@ class QFormerEngine:
         keep, table = [], []
         for name, value in state.items():
             t = value if isinstance(value, torch.Tensor) else torch.as_tensor(value)
+            if name == "query_tokens" and t.dim() == 3:
+                t = t[0]  # [1, K, hidden] parameter of the reference (cambrian_arch.py:420-423)
             if not t.dtype.is_floating_point or t.dim() not in (1, 2):
                 continue  # e.g. embeddings.position_ids
             t = t.detach().to(self.device).contiguous()
@@ -222,6 +224,159 @@ class QFormerEngine:
                 out_dev.record_stream(self._d2h_stream)
         cur.wait_stream(self._d2h_stream)
         for t in stage:
+            t.record_stream(self._h2d_stream)
+        return out_host
+
+    # -- the upstream entry: from the towers' outputs -----------------------------------------
+    def _frames_workspace(self, n_chunks, rows, Tv, Ta, K, T) -> torch.Tensor:
+        most = max(rows, n_chunks, 1)
+        need = int(self.lib.tdc_frames_workspace_bytes(self._h, n_chunks, rows, most, Tv, Ta, K, T))
+        floor = int(self.lib.tdc_frames_workspace_bytes(self._h, n_chunks, rows, 1, Tv, Ta, K, T))
+        want = max(min(need, self.max_workspace_bytes), floor)
+        if self._ws is None or self._ws.numel() < want:
+            self._ws = None
+            self._ws = torch.empty(want, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def compress_frames(self, frames: torch.Tensor, static_frames: torch.Tensor, row_frames: torch.Tensor,
+                        row_chunk: torch.Tensor, *, audio: Optional[torch.Tensor] = None,
+                        input_ids: Optional[torch.Tensor] = None, num_query: int = 16, learned_queries: bool = False,
+                        fold: bool = True, want_static: bool = True, out_dtype=torch.bfloat16,
+                        multicast_ptr: Optional[int] = None):
+        """The TDC stage from the towers' outputs (tdc_compress_frames): mm_projector, image_newline, audio_proj,
+        query build, Q-Former, vision_proj + L2-normalise for all chunks of a video in one call.
+
+        frames [n_frames, Tv, d_frame_in] bf16 (input of mm_projector), audio [n_frames, Ta, d_audio] bf16 or None,
+        static_frames [C] / row_frames [R] / row_chunk [R] int32 (see compressor.plan_chunks).
+        Returns (static_out [C, side*(side+1)+Ta, d] or None, compressed [R, K, d])."""
+        if self.cfg.d_frame_in <= 0:
+            raise RuntimeError("engine was created without d_frame_in: no upstream entry")
+        dev = self.device
+        if not frames.is_cuda:
+            raise RuntimeError("compress_frames needs CUDA tensors: there is no CPU fallback")
+        frames = frames.to(dev, torch.bfloat16).contiguous()
+        n_frames, Tv, d_in = frames.shape
+        if d_in != self.cfg.d_frame_in:
+            raise ValueError(f"frames width {d_in} vs d_frame_in {self.cfg.d_frame_in}")
+        Ta = 0
+        if audio is not None:
+            audio = audio.to(dev, torch.bfloat16).contiguous()
+            if audio.shape[0] != n_frames or audio.shape[2] != self.cfg.d_audio:
+                raise ValueError("audio must be [n_frames, Ta, d_audio]")
+            Ta = int(audio.shape[1])
+        sf = static_frames.to(dev, torch.int32).contiguous()
+        rf = row_frames.to(dev, torch.int32).contiguous()
+        rc_ = row_chunk.to(dev, torch.int32).contiguous()
+        C_, R = int(sf.numel()), int(rf.numel())
+        T = 0 if input_ids is None else int(input_ids.shape[-1])
+        ids = None if T == 0 else input_ids.reshape(1, T).to(dev, torch.int64).contiguous()
+        side = int(round(Tv ** 0.5))
+        d = self.cfg.d_out
+        static_out = torch.empty((C_, side * (side + 1) + Ta, d), dtype=out_dtype, device=dev) if want_static else None
+        out = None if multicast_ptr is not None else torch.empty((R, num_query, d), dtype=out_dtype, device=dev)
+        if C_ == 0 and R == 0:
+            return static_out, out
+        ws = self._frames_workspace(C_, R, Tv, Ta, num_query, T)
+        a = TdcFramesArgs(frames.data_ptr(), None if audio is None else audio.data_ptr(), sf.data_ptr(), rf.data_ptr(),
+                          rc_.data_ptr(), None if ids is None else ids.data_ptr(), n_frames, C_, R, Tv, Ta, num_query,
+                          T, int(learned_queries), int(fold), int(multicast_ptr is not None), _DTYPES[out_dtype],
+                          None if static_out is None else static_out.data_ptr(),
+                          int(multicast_ptr) if multicast_ptr is not None else out.data_ptr())
+        with torch.cuda.device(dev):
+            rc = self.lib.tdc_compress_frames(self._h, C.byref(a), _ptr(ws), ws.numel(), _stream(dev))
+        check(rc, self._h, "tdc_compress_frames")
+        return static_out, out
+
+    def compress_frames_host(self, frames_host: torch.Tensor, audio_host: Optional[torch.Tensor], chunk_start,
+                             chunk_len, out_host: Optional[torch.Tensor] = None, *, input_ids=None, num_query: int = 16,
+                             learned_queries: bool = False, fold: bool = True, keep_static: bool = True,
+                             static_out: Optional[torch.Tensor] = None, chunks_per_batch: int = 256,
+                             out_device: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`compress_frames` for tower outputs that live in (pinned) HOST memory, in video order: contiguous
+        ranges of whole chunks are streamed to the GPU on a copy stream while the previous range computes, each
+        range's compressed tokens go back to `out_host` on a third stream.  This is the end-to-end entry of the
+        path: what crosses PCIe is what the towers produce (1024-wide features + 768-wide audio tokens), not the
+        d_llm-wide projected tokens.
+
+        chunk_start / chunk_len: first frame and frame count (1..8) of every chunk, ascending and contiguous per
+        range (compressor.plan_chunks); the first frame of a chunk is its key frame, the others are rows.
+        `static_out` [C, Ls, d] (device) receives the key frames' pass-through tokens when given."""
+        import numpy as np
+        dev = self.device
+        cs = np.asarray(chunk_start, dtype=np.int64)
+        cl = np.asarray(chunk_len, dtype=np.int64)
+        Cn = len(cs)
+        rows_per_chunk = cl - 1 if keep_static else cl
+        row_base = np.concatenate([[0], np.cumsum(rows_per_chunk)])
+        R = int(row_base[-1])
+        K, d = num_query, self.cfg.d_out
+        if out_host is None:
+            out_host = torch.empty((R, K, d), dtype=torch.bfloat16, pin_memory=True)
+        if Cn == 0:
+            return out_host
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_h2d_stream"):
+            self._h2d_stream, self._d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        # ranges of chunks; taper the tail so that the last range's compute + read-back is short
+        bounds, c0 = [], 0
+        cb = max(1, min(chunks_per_batch, Cn))
+        while Cn - c0 > cb:
+            bounds.append((c0, c0 + cb)); c0 += cb
+        while Cn - c0 > max(cb // 8, 1):
+            step = (Cn - c0) // 2
+            bounds.append((c0, c0 + step)); c0 += step
+        if c0 < Cn:
+            bounds.append((c0, Cn))
+        max_frames = max(int(cs[b - 1] + cl[b - 1] - cs[a]) for a, b in bounds)
+        Tv, d_in = frames_host.shape[1], frames_host.shape[2]
+        stage_f = [torch.empty((max_frames, Tv, d_in), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        stage_a = None
+        if audio_host is not None:
+            stage_a = [torch.empty((max_frames,) + tuple(audio_host.shape[1:]), dtype=torch.bfloat16, device=dev)
+                       for _ in range(2)]
+        h2d_done = [torch.cuda.Event() for _ in range(2)]
+        compute_done = [torch.cuda.Event() for _ in range(2)]
+        ids_dev = None if input_ids is None else input_ids.to(dev)
+        self._h2d_stream.wait_stream(cur)
+        for i, (a, b) in enumerate(bounds):
+            sb = i % 2
+            f0, f1 = int(cs[a]), int(cs[b - 1] + cl[b - 1])
+            # integer plan of the range, relative to its first frame
+            st = (cs[a:b] - f0).astype(np.int32)
+            if keep_static:
+                rf = np.concatenate([np.arange(s + 1, s + n, dtype=np.int32) for s, n in zip(st, cl[a:b])]) \
+                    if int(rows_per_chunk[a:b].sum()) else np.zeros(0, np.int32)
+            else:
+                rf = np.concatenate([np.arange(s, s + n, dtype=np.int32) for s, n in zip(st, cl[a:b])])
+            rck = np.repeat(np.arange(b - a, dtype=np.int32), rows_per_chunk[a:b])
+            with torch.cuda.stream(self._h2d_stream):
+                if i >= 2:
+                    self._h2d_stream.wait_event(compute_done[sb])
+                stage_f[sb][: f1 - f0].copy_(frames_host[f0:f1], non_blocking=True)
+                if stage_a is not None:
+                    stage_a[sb][: f1 - f0].copy_(audio_host[f0:f1], non_blocking=True)
+                plan_dev = [torch.from_numpy(x).to(dev, non_blocking=True) for x in (st, rf, rck)]
+                h2d_done[sb].record(self._h2d_stream)
+            cur.wait_event(h2d_done[sb])
+            s_out, comp = self.compress_frames(stage_f[sb][: f1 - f0], plan_dev[0], plan_dev[1], plan_dev[2],
+                                               audio=None if stage_a is None else stage_a[sb][: f1 - f0],
+                                               input_ids=ids_dev, num_query=K, learned_queries=learned_queries,
+                                               fold=fold, want_static=static_out is not None,
+                                               out_dtype=out_host.dtype)
+            for t in plan_dev:
+                t.record_stream(cur)
+            r0, r1 = int(row_base[a]), int(row_base[b])
+            if static_out is not None:
+                static_out[a:b].copy_(s_out)
+            if out_device is not None:
+                out_device[r0:r1].copy_(comp)
+            compute_done[sb].record(cur)
+            with torch.cuda.stream(self._d2h_stream):
+                self._d2h_stream.wait_event(compute_done[sb])
+                out_host[r0:r1].copy_(comp, non_blocking=True)
+                comp.record_stream(self._d2h_stream)
+        cur.wait_stream(self._d2h_stream)
+        for t in stage_f + (stage_a or []):
             t.record_stream(self._h2d_stream)
         return out_host
 

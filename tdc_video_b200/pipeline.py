@@ -39,10 +39,11 @@ def append_newline_tokens(frame_tokens: torch.Tensor, image_newline: torch.Tenso
 
 
 @torch.no_grad()
-def tdc_video_stage(compressor: TDCCompressor, visual_emb_frame: torch.Tensor, dino_features: torch.Tensor, *,
+def tdc_video_stage(compressor: TDCCompressor, visual_emb_frame: Optional[torch.Tensor], dino_features: torch.Tensor, *,
                     input_ids: Optional[torch.Tensor] = None, audio_windows: Optional[Sequence[torch.Tensor]] = None,
                     sample_indices=None, max_visual_len: Optional[int] = None, max_num_segments: int = 24,
-                    shard: bool = False, return_segments: bool = False):
+                    shard: bool = False, return_segments: bool = False,
+                    tower_features: Optional[torch.Tensor] = None, fold: bool = True):
     """One video through adaptive segmentation and TDC compression.
 
     visual_emb_frame [n_frames, Lv, d_llm]  projected frame tokens incl. newline tokens (CUDA)
@@ -51,7 +52,16 @@ def tdc_video_stage(compressor: TDCCompressor, visual_emb_frame: torch.Tensor, d
     input_ids        [1, T]                 BERT ids of the prompt (text_input mode)
     audio_windows / sample_indices          BEATs features [1, t, 768] of the 10-second windows and the 0/1
                                             "a frame was sampled in this second" flags (:1547-1598); None = silent
+    tower_features   [n_frames, Tv, C]      ALTERNATIVE to visual_emb_frame (pass None there): the concatenated tower
+                                            features, i.e. the INPUT of mm_projector (:1149); the projector, the
+                                            newline tokens and everything after run in one tdc_compress_frames call
+                                            (`compressor` built with mm_input_size=C; `fold` see the C header)
     Returns the visual token sequence [tokens, d_llm] (and, if asked, the selected frames / boundaries)."""
+    from_towers = tower_features is not None
+    if from_towers:
+        if visual_emb_frame is not None:
+            raise ValueError("pass either visual_emb_frame or tower_features")
+        visual_emb_frame = tower_features
     if not visual_emb_frame.is_cuda or not dino_features.is_cuda:
         raise RuntimeError("tdc_video_stage needs CUDA tensors: there is no CPU fallback")
     if visual_emb_frame.shape[0] != dino_features.shape[0]:
@@ -73,8 +83,12 @@ def tdc_video_stage(compressor: TDCCompressor, visual_emb_frame: torch.Tensor, d
             kept[pos[selected]] = 1
             si = kept
         audio_frames = pool_audio_per_frame(audio_windows, si, n)
-    seq = compressor.compress_video(visual_emb_frame, sizes, input_ids=input_ids, audio_frames=audio_frames,
-                                    max_visual_len=max_visual_len, shard=shard)
+    if from_towers:
+        seq = compressor.compress_video_from_towers(visual_emb_frame, sizes, input_ids=input_ids,
+                                                    audio_frames=audio_frames, max_visual_len=max_visual_len, fold=fold)
+    else:
+        seq = compressor.compress_video(visual_emb_frame, sizes, input_ids=input_ids, audio_frames=audio_frames,
+                                        max_visual_len=max_visual_len, shard=shard)
     if return_segments:
         return seq, selected, boundaries
     return seq

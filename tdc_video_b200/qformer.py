@@ -142,7 +142,8 @@ class TDCBertModel(nn.Module):
         """Cheap fingerprint of in-place edits: every parameter's autograd version counter."""
         return sum(int(p._version) for p in self.parameters())
 
-    def engine(self, d_out: int = 0, extra_state=None, extra_key=None) -> QFormerEngine:
+    def engine(self, d_out: int = 0, extra_state=None, extra_key=None, d_frame_in: int = 0,
+               d_audio: int = 0) -> QFormerEngine:
         """The libtdc handle holding this module's weights (rebuilt when they move/change).
         `extra_state` adds sibling tensors (vision_proj.*); `extra_key` identifies their version.
         A handle that carries vision_proj also serves the plain `.bert(...)` forward (d_out = 0 requests reuse
@@ -151,7 +152,7 @@ class TDCBertModel(nn.Module):
         if d_out == 0 and extra_state is None and self._engine is not None and self._engine_key is not None \
                 and self._engine_key[0] == p.device and self._engine_key[3] == self._weights_version():
             return self._engine
-        key = (p.device, d_out, extra_key, self._weights_version())
+        key = (p.device, d_out, extra_key, self._weights_version(), d_frame_in, d_audio)
         if self._engine is None or self._engine_key != key:
             if p.device.type != "cuda":
                 raise RuntimeError("TDCBertModel runs on a CUDA (sm_100a) device only: move the module to the GPU; "
@@ -163,7 +164,8 @@ class TDCBertModel(nn.Module):
                                          intermediate=c.intermediate_size, layers=c.num_hidden_layers,
                                          cross_freq=c.cross_attention_freq, d_enc=c.encoder_width, d_out=d_out,
                                          vocab=c.vocab_size, max_pos=c.max_position_embeddings,
-                                         ln_eps=c.layer_norm_eps, device=p.device)
+                                         ln_eps=c.layer_norm_eps, device=p.device, d_frame_in=d_frame_in,
+                                         d_audio=d_audio)
             state = {k: v for k, v in self.state_dict().items() if v.dtype.is_floating_point}
             if extra_state:
                 state.update(extra_state)

@@ -121,6 +121,28 @@ def make_inputs(geom: QFormerGeometry, seed: int, rows: int, kv_tokens: int, num
     return {"query_embeds": q, "enc": enc, "input_ids": ids}
 
 
+def make_frontend_state_dict(d_llm: int, d_frame_in: int, d_audio: int, hidden: int, seed: int,
+                             num_query: int = 16) -> Dict[str, np.ndarray]:
+    """The sibling tensors of the upstream ("frames") entry under the reference's names: `mm_projector.{0,2}.*`
+    (cambrian_arch.py:65-69), `image_newline` (:148), `query_proj.*` (:484), `query_tokens` (:420-423) and, with
+    d_audio > 0, `audio_proj.*` (:180-181).  Scales are chosen so that N(0,1) tower features give projected
+    tokens of about unit variance and N(0, 0.25) audio features give audio tokens of variance 0.25 — the
+    statistics `make_inputs` uses for already-projected tokens."""
+    rs = np.random.RandomState(seed)
+    f = lambda shape, scale: (rs.standard_normal(shape) * scale).astype(np.float32)
+    sd = {
+        "mm_projector.0.weight": f((d_llm, d_frame_in), 1.0 / np.sqrt(d_frame_in)), "mm_projector.0.bias": f((d_llm,), 0.02),
+        "mm_projector.2.weight": f((d_llm, d_llm), 1.0 / np.sqrt(0.425 * d_llm)), "mm_projector.2.bias": f((d_llm,), 0.02),
+        "image_newline": f((d_llm,), 0.5),
+        "query_proj.weight": f((hidden, d_llm), 0.02), "query_proj.bias": f((hidden,), 0.02),
+        "query_tokens": f((1, num_query, hidden), 0.02),
+    }
+    if d_audio > 0:
+        sd["audio_proj.weight"] = f((d_llm, d_audio), 1.0 / np.sqrt(d_audio))
+        sd["audio_proj.bias"] = f((d_llm,), 0.02)
+    return sd
+
+
 # ---- Spatial Vision Aggregator (SURVEY §8f-3) -----------------------------------------------------------------
 def make_sva_state_dict(hidden: int, tower_dims, window_sides, num_layers: int, seed: int, stress: float = 1.0
                         ) -> Dict[str, np.ndarray]:

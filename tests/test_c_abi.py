@@ -35,7 +35,7 @@ def test_python_binding_lists_the_same_symbols():
 
 
 def test_abi_version_and_null_handling(lib):
-    assert lib.tdc_abi_version() == 1
+    assert lib.tdc_abi_version() == 2
     lib.tdc_last_error.restype = ctypes.c_char_p
     lib.tdc_create.restype = ctypes.c_int
     assert lib.tdc_create(None, None) == -1          # TDC_EINVAL, no crash

@@ -1,0 +1,208 @@
+"""The upstream entry (tdc_compress_frames: tower features in, TDC token sequence out) on the GPU against
+ (1) committed outputs of the reference's REAL prepare_inputs_labels_for_multimodal run with the GELU-MLP
+     projector (tests/golden/towers_*.npz), in both weight modes (fold = 1 / 0);
+ (2) the CPU oracle at the shipped widths (hidden 768, 12 heads, d_llm 3584, 1024-wide tower features, audio);
+ (3) itself: host streaming == device-resident call, folded == unfolded within the tolerance.
+Tolerance as everywhere: per-token cosine >= 0.999, both relative errors <= 2e-2."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import driver_oracle
+from oracle import qformer_oracle as oracle
+from oracle.make_golden import DRIVER_D, DRIVER_GEOM, driver_audio, driver_tables, driver_weights_mlp
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "towers_*.npz")))
+
+
+def _ok(test, ref, what):
+    m = oracle.parity_metrics(test.float().cpu(), ref)
+    print(what, m)
+    assert m["min_cos"] >= 0.999 and m["max_abs_over_max_ref"] <= 2e-2 and m["max_tok_rel_l2"] <= 2e-2, (what, m)
+    return m
+
+
+def _compressor(m, w, d_in):
+    from tdc_video_b200.compressor import TDCCompressor
+    from tdc_video_b200.qformer import QFormerConfig
+    g = DRIVER_GEOM
+    cfg = QFormerConfig(vocab_size=g.vocab, hidden_size=g.hidden, num_hidden_layers=g.layers,
+                        num_attention_heads=g.heads, intermediate_size=g.intermediate,
+                        max_position_embeddings=g.max_pos, layer_norm_eps=g.ln_eps,
+                        cross_attention_freq=g.cross_freq, encoder_width=DRIVER_D, query_length=m["num_query"])
+    comp = TDCCompressor(DRIVER_D, context_token_num=m["num_query"], query_type=m["query_type"], text_input=m["text"],
+                         add_static=m["add_static"], audio_input=bool(m.get("audio")), qformer_config=cfg,
+                         mm_input_size=d_in)
+    sd = {}
+    for k, v in w.items():
+        if k.startswith(("embeddings.", "encoder.")):
+            sd["Qformer.bert." + k] = torch.from_numpy(v)
+        elif k.split(".")[0] in ("vision_proj", "query_proj", "frame_seg", "query_tokens", "audio_proj", "mm_projector",
+                                 "image_newline"):
+            sd[k] = torch.from_numpy(v)
+    missing, unexpected = comp.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all("position_ids" in k or k.startswith("Qformer.cls.") for k in missing), missing
+    return comp.cuda().eval()
+
+
+@pytest.mark.parametrize("fold", [True, False], ids=["fold", "literal"])
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[7:-4] for p in GOLDEN])
+def test_frames_stage_matches_the_reference_driver(path, fold):
+    """adapt_segment -> tdc_compress_frames -> assembly, against the real reference function's token sequence."""
+    from tdc_video_b200.pipeline import tdc_video_stage
+    z = np.load(path)
+    m = json.loads(str(z["meta"]))
+    w = driver_weights_mlp(m["weight_seed"], m["num_query"])
+    sig, dino = driver_tables(m["table_seed"], m["n_frames"])
+    n = m["n_frames"]
+    audio_kw = {}
+    if m.get("audio"):
+        windows, flags, _, proj = driver_audio(m["audio_seed"], n, m["audio"])
+        w.update(proj)
+        audio_kw = dict(audio_windows=[torch.from_numpy(a).cuda() for a in windows], sample_indices=flags)
+    feats = torch.from_numpy(np.concatenate([sig, dino], -1)).cuda()          # the input of mm_projector (:1149)
+    comp = _compressor(m, w, feats.shape[-1])
+    ids = torch.tensor([m["prompt_ids"]], device="cuda")
+    seq, selected, bounds = tdc_video_stage(comp, None, torch.from_numpy(dino).cuda(), input_ids=ids,
+                                            max_visual_len=m["max_visual_len"], return_segments=True,
+                                            tower_features=feats, fold=fold, **audio_kw)
+    torch.cuda.synchronize()
+    assert bounds.cpu().tolist() == z["segment_frame_indices"].tolist()
+    ref = torch.from_numpy(z["visual_tokens"])
+    assert tuple(seq.shape) == tuple(ref.shape)
+    _ok(seq, ref, f"{os.path.basename(path)} fold={fold}")
+
+
+def _full_problem(seed, n_frames, chunk, audio=True, T=0, d=3584, d_in=1024):
+    """Shipped widths: state dict + tower features + audio tokens + a plan of `chunk`-frame chunks."""
+    from tdc_video_b200.synth import QFormerGeometry, make_frontend_state_dict, make_state_dict
+    geom = QFormerGeometry(d_enc=d, d_out=d, vocab=30522 if T else 0)
+    sd = make_state_dict(geom, seed, stress=2.0, with_text=T > 0)
+    sd.update(make_frontend_state_dict(d, d_in, 768 if audio else 0, geom.hidden, seed + 1))
+    rs = np.random.RandomState(seed + 2)
+    frames = rs.standard_normal((n_frames, 144, d_in)).astype(np.float32)
+    aud = (rs.standard_normal((n_frames, 50, 768)) * 0.5).astype(np.float32) if audio else None
+    sizes = [chunk] * (n_frames // chunk) + ([n_frames % chunk] if n_frames % chunk else [])
+    return geom, sd, frames, aud, sizes
+
+
+def _oracle_frames(sd, geom, frames, aud, sizes, K, ids=None):
+    """CPU oracle of the frames stage on bf16-rounded inputs: (static tokens per chunk, compressed rows)."""
+    t = lambda k: torch.from_numpy(sd[k])
+    x = torch.from_numpy(frames).bfloat16().float()
+    xv = oracle.gelu_mlp(t("mm_projector.0.weight"), t("mm_projector.0.bias"), t("mm_projector.2.weight"),
+                         t("mm_projector.2.bias"), x)
+    n = xv.shape[0]
+    nl = t("image_newline").view(1, 1, 1, -1).expand(n, 12, 1, -1)
+    fr = torch.cat([xv.view(n, 12, 12, -1), nl], dim=2).flatten(1, 2)                      # [n, 156, d]
+    full = fr
+    if aud is not None:
+        a = torch.from_numpy(aud).bfloat16().float()
+        full = torch.cat([fr, torch.nn.functional.linear(a, t("audio_proj.weight"), t("audio_proj.bias"))], dim=1)
+    statics, comps = [], []
+    f0 = 0
+    sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
+    for s in sizes:
+        for c0 in range(f0, f0 + s, 8):
+            c1 = min(c0 + 8, f0 + s)
+            statics.append(full[c0])
+            if c1 - c0 > 1:
+                q = oracle.avg_pool_queries(fr[c0][None], K)
+                q = torch.nn.functional.linear(q, t("query_proj.weight"), t("query_proj.bias")).expand(c1 - c0 - 1, -1, -1)
+                i = None if ids is None else ids.expand(c1 - c0 - 1, -1)
+                comps.append(oracle.compress(sd_t, geom, q, full[c0 + 1:c1], i))
+        f0 += s
+    return torch.stack(statics), torch.cat(comps)
+
+
+def _engine(geom, sd, d_in, audio, T=0):
+    from tdc_video_b200 import QFormerEngine
+    eng = QFormerEngine(d_enc=geom.d_enc, d_out=geom.d_out, vocab=30522 if T else 0, d_frame_in=d_in,
+                        d_audio=768 if audio else 0)
+    eng.load_weights(sd)
+    return eng
+
+
+def _plan(sizes):
+    from tdc_video_b200.compressor import plan_chunks
+    p = plan_chunks(sizes, True)
+    i32 = lambda a: torch.from_numpy(a.astype(np.int32))
+    return p, i32(p.static_frames), i32(p.row_frames), i32(p.row_chunk)
+
+
+@pytest.mark.parametrize("fold", [True, False], ids=["fold", "literal"])
+def test_frames_entry_full_widths_against_oracle(fold):
+    geom, sd, frames, aud, sizes = _full_problem(11, 22, 4)      # 5 chunks of 4 + one of 2 -> 16 rows, 6 key frames
+    eng = _engine(geom, sd, 1024, True)
+    p, sf, rf, rc = _plan(sizes)
+    st, comp = eng.compress_frames(torch.from_numpy(frames).cuda().bfloat16(), sf, rf, rc,
+                                   audio=torch.from_numpy(aud).cuda().bfloat16(), fold=fold, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    ref_st, ref_comp = _oracle_frames(sd, geom, frames, aud, sizes, 16)
+    assert tuple(st.shape) == tuple(ref_st.shape) == (6, 206, 3584)
+    assert tuple(comp.shape) == tuple(ref_comp.shape) == (16, 16, 3584)
+    _ok(st, ref_st, f"static fold={fold}")
+    _ok(comp, ref_comp, f"compressed fold={fold}")
+    norms = comp.float().norm(dim=-1)
+    assert torch.allclose(norms, torch.ones_like(norms), atol=2e-3)
+
+
+def test_frames_entry_text_and_ragged_chunks():
+    """A shared prompt (text_input mode), chunks of 8 / 1 / 3 frames (a single-frame chunk has no rows)."""
+    geom, sd, frames, aud, _ = _full_problem(12, 12, 8, audio=False, T=6)
+    sizes = [8, 1, 3]
+    eng = _engine(geom, sd, 1024, False, T=6)
+    ids = torch.randint(1000, 30000, (1, 6), generator=torch.Generator().manual_seed(3))
+    p, sf, rf, rc = _plan(sizes)
+    assert p.num_chunks == 3 and p.num_rows == 9
+    st, comp = eng.compress_frames(torch.from_numpy(frames).cuda().bfloat16(), sf, rf, rc, input_ids=ids.cuda(),
+                                   out_dtype=torch.float32)
+    ref_st, ref_comp = _oracle_frames(sd, geom, frames, None, sizes, 16, ids)
+    assert tuple(st.shape) == (3, 156, 3584)
+    _ok(st, ref_st, "static text")
+    _ok(comp, ref_comp, "compressed text")
+
+
+def test_frames_small_workspace_and_host_streaming_give_the_same_bits():
+    """Row batching inside the call (a workspace for 5 items) and the host-streaming entry (ranges of 2 chunks)
+    are invisible: rows are independent."""
+    geom, sd, frames, aud, sizes = _full_problem(13, 23, 4)
+    eng = _engine(geom, sd, 1024, True)
+    p, sf, rf, rc = _plan(sizes)
+    f_dev, a_dev = torch.from_numpy(frames).cuda().bfloat16(), torch.from_numpy(aud).cuda().bfloat16()
+    st, comp = eng.compress_frames(f_dev, sf, rf, rc, audio=a_dev)
+    small = int(eng.lib.tdc_frames_workspace_bytes(eng._h, p.num_chunks, p.num_rows, 5, 144, 50, 16, 0))
+    eng._ws, eng.max_workspace_bytes = None, small
+    st2, comp2 = eng.compress_frames(f_dev, sf, rf, rc, audio=a_dev)
+    assert eng._ws.numel() == small
+    assert torch.equal(st, st2) and torch.equal(comp, comp2)
+    eng._ws, eng.max_workspace_bytes = None, 8 << 30
+    chunk_start = p.static_frames
+    out_host = torch.empty((p.num_rows, 16, 3584), dtype=torch.bfloat16, pin_memory=True)
+    st3 = torch.empty_like(st)
+    eng.compress_frames_host(torch.from_numpy(frames).bfloat16().pin_memory(), torch.from_numpy(aud).bfloat16().pin_memory(),
+                             chunk_start, p.chunk_len, out_host, static_out=st3, chunks_per_batch=2)
+    torch.cuda.synchronize()
+    assert torch.equal(out_host.cuda(), comp) and torch.equal(st3, st)
+
+
+def test_frames_entry_errors():
+    from tdc_video_b200 import QFormerEngine, TdcError
+    from tdc_video_b200.synth import QFormerGeometry, make_state_dict
+    geom = QFormerGeometry(hidden=128, heads=2, intermediate=256, layers=2, cross_freq=2, d_enc=64, d_out=64, vocab=0)
+    eng = QFormerEngine(hidden=128, heads=2, intermediate=256, layers=2, cross_freq=2, d_enc=64, d_out=64,
+                        d_frame_in=32)
+    eng.load_weights(make_state_dict(geom, 1, with_text=False))     # no mm_projector / newline / query_proj tensors
+    z = torch.zeros(1, dtype=torch.int32)
+    with pytest.raises(TdcError):
+        eng.compress_frames(torch.zeros(2, 16, 32, device="cuda", dtype=torch.bfloat16), z, z + 1, z)
+    with pytest.raises(RuntimeError):
+        QFormerEngine(hidden=128, heads=2, intermediate=256, layers=2, cross_freq=2, d_enc=64, d_out=64).compress_frames(
+            torch.zeros(2, 16, 32, device="cuda", dtype=torch.bfloat16), z, z + 1, z)
