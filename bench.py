@@ -5,21 +5,27 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...      # the reference algorithm on the host CPU cores
 
-One "step" = one pass of the hot path over one synthetic video per GPU: for every dynamic
-frame (row) the Q-Former (12 layers, cross-attention to the frame's L KV tokens) + vision_proj
-+ L2-normalise, i.e. tdc/cambrian_arch.py:1603-1692 for all chunks at once, then (N > 1) the
-all-gather of the compressed tokens so that every rank holds the ordered sequence (fused into the
-final kernel through NVSwitch multicast stores; `--no-multicast` = NCCL all-gather).
+One "step" = one pass of the hot path over one synthetic video per GPU, in the reference's order
+(tdc/cambrian_arch.py): mm_projector on every frame's tower features (:1149), image_newline (:1269-1281),
+audio_proj (:1611-1614), query build from the key frame (:1629-1640), the Q-Former on every dynamic frame
+(:1653-1662), vision_proj + L2-normalise (:1664-1667) — for all chunks at once through ONE library entry
+(`tdc_compress_frames`, --entry frames, the default) — then (N > 1) the all-gather of the compressed tokens
+so that every rank holds the ordered sequence (fused into the final kernel through NVSwitch multicast stores;
+`--no-multicast` = NCCL all-gather).
 
- * `value`  : whole-job video-seconds/s, inputs resident in HBM, CUDA-event timed, max over ranks
- * `e2e`    : the same through `QFormerEngine.compress_host` with the KV tokens in pinned HOST
-              memory (H2D of every row inside the timed region, result copied back to host)
- * `roofline`: dominant kernel = the cross-attention K/V projection GEMM (tcgen05), algorithmic
-              FLOPs / its CUDA-event time (events on the launching stream, recorded by the library)
+ * `value`  : whole-job video-seconds/s, the towers' outputs resident in HBM, CUDA-event timed, max over ranks
+ * `e2e`    : the same through `QFormerEngine.compress_frames_host` with the towers' outputs in pinned HOST
+              memory (H2D of every frame inside the timed region, compressed tokens copied back to the host)
+ * `roofline`: dominant kernel = the cross-attention K/V projection GEMM (tcgen05), EXECUTED FLOPs / its
+              CUDA-event time (events on the launching stream, recorded by the library)
+ * `path`   : model FLOPs (reference formulation) and executed FLOPs (after weight folding) per step
+ * `unfolded`: the same step with every projection executed as the reference orders them (fold = 0)
+ * `qformer_only`: round 1's line — Q-Former + vision_proj on already projected tokens resident in HBM
+              (`--entry tokens` runs only that; the variant workloads use it)
  * `cpu_baseline`: the reference algorithm (oracle port, fp32 torch) on the host cores, bounded sample
 
 Synthetic data, random-init weights (tdc_video_b200/synth.py statistics); weak scaling: every GPU
-compresses its own `segments` video-seconds.
+compresses its own `segments` video-seconds; `strong` = ONE video sharded over the N GPUs.
 """
 from __future__ import annotations
 
@@ -75,6 +81,23 @@ def flops_per_row(L, d_enc, K, T, d_out, projector="vision_proj"):
     rest = (LAYERS * (8 * n * H * H + 4 * n * n * H) + N_CROSS * (4 * K * H * H + 4 * K * L * H)
             + LAYERS * 4 * K * H * I + LAYERS * 4 * T * H * I + proj)
     return kv + rest, kv
+
+
+def frames_flops(w, tv=144, d_in=1024, d_audio=768):
+    """Per video-second of the frames entry: (model FLOPs in the reference formulation, executed FLOPs with the
+    folded weights, executed FLOPs of the K/V projection GEMMs alone)."""
+    F_, L, d, K, T = w["frames_per_segment"], w["kv_tokens"], w["d_enc"], w["num_query"], w.get("num_text", 0)
+    ta = w["audio_tokens"]
+    f_row, f_row_kv = flops_per_row(L, d, K, T, w["d_out"])
+    proj_frame = 2 * tv * (d_in * d + d * d)                    # mm_projector, every frame (:1149)
+    audio_frame = 2 * ta * d_audio * d                          # audio_proj, every frame (:1613)
+    query_chunk = 2 * K * d * H                                 # query_proj, once per chunk (:1638)
+    model = F_ * (proj_frame + audio_frame) + query_chunk + (F_ - 1) * f_row
+    kv_exec_row = 2 * tv * d * 2 * H * N_CROSS + 2 * ta * d_audio * 2 * H * N_CROSS      # folded K/V GEMMs
+    executed = (F_ * 2 * tv * d_in * d                          # mm_projector.0 on every frame
+                + 2 * tv * d * d + audio_frame + query_chunk    # key frame: mm_projector.2, audio_proj, query_proj
+                + (F_ - 1) * (f_row - f_row_kv + kv_exec_row))
+    return model, executed, (F_ - 1) * kv_exec_row
 
 
 def measured_traffic_per_row():
@@ -175,11 +198,48 @@ def build_problem(w, seed):
         sd["mm_projector.0.bias"] = (rs.standard_normal(d) * 0.02).astype(np.float32)
         sd["mm_projector.2.weight"] = (rs.standard_normal((d, d)) * 0.02).astype(np.float32)
         sd["mm_projector.2.bias"] = (rs.standard_normal(d) * 0.02).astype(np.float32)
+    if w.get("entry") == "frames":
+        from tdc_video_b200.synth import make_frontend_state_dict
+        sd.update(make_frontend_state_dict(w["d_enc"], w["d_frame_in"], 768 if w["audio_tokens"] else 0, geom.hidden,
+                                           seed + 29, w["num_query"]))
     rows = w["segments"] * (w["frames_per_segment"] - 1)
     return geom, sd, rows
 
 
+def cpu_baseline_frames(geom, sd, w, sample_rows, seed, passes=1):
+    """The reference algorithm of the frames entry (oracle/frames_oracle.py: mm_projector, newline, audio_proj,
+    query build, Q-Former, vision_proj + normalise), fp32 torch on all host cores, all sampled rows in ONE call."""
+    from oracle import frames_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    F_ = w["frames_per_segment"]
+    segs = max(1, sample_rows // (F_ - 1))
+    rs = np.random.RandomState(seed)
+    frames = torch.from_numpy(rs.standard_normal((segs * F_, 144, w["d_frame_in"])).astype(np.float32))
+    audio = None
+    if w["audio_tokens"]:
+        audio = torch.from_numpy((rs.standard_normal((segs * F_, w["audio_tokens"], 768)) * 0.5).astype(np.float32))
+    T = w.get("num_text", 0)
+    ids = None if T == 0 else torch.from_numpy(rs.randint(1000, 30000, size=(1, T)))
+    sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
+    cs, cl = np.arange(segs) * F_, np.full(segs, F_)
+    with torch.no_grad():
+        frames_oracle.frames_stage(sd_t, geom, frames[:F_], None if audio is None else audio[:F_], cs[:1], cl[:1],
+                                   w["num_query"], ids)                                   # warm-up
+        t0 = time.perf_counter()
+        for _ in range(passes):
+            frames_oracle.frames_stage(sd_t, geom, frames, audio, cs, cl, w["num_query"], ids)
+        dt = time.perf_counter() - t0
+    return passes * segs / dt, dt, cores
+
+
 def cpu_baseline(geom, sd, w, sample_rows, seed, passes=1):
+    if w.get("entry") == "frames":
+        return cpu_baseline_frames(geom, sd, w, sample_rows, seed, passes)
+    return cpu_baseline_tokens(geom, sd, w, sample_rows, seed, passes)
+
+
+def cpu_baseline_tokens(geom, sd, w, sample_rows, seed, passes=1):
     """The reference algorithm (oracle port of tdc/Qformer.py + vision_proj + normalize), fp32 torch on
     all host cores, batched as ONE call (kinder to the CPU than the reference's <= 7-row loop)."""
     from oracle import qformer_oracle as oracle
@@ -243,7 +303,9 @@ def run_reference_arm(args, w):
         "impl": "reference", "metric": "video_seconds_per_sec", "value": value, "unit": "video-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(dts),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": w["label"], "rows_per_step_sample": sample * passes},
+        "config": {"workload": args.workload, "desc": w["label"], "rows_per_step_sample": sample * passes,
+                   "entry": "frames (oracle/frames_oracle.py: mm_projector, newline, audio_proj, query build, Q-Former, "
+                            "vision_proj)" if w.get("entry") == "frames" else "tokens (oracle/qformer_oracle.py)"},
         "cpu_baseline": {"value": value, "unit": "video-s/s", "cores": cores, "kind": "port",
                          "sample": f"{passes} x {sample} rows (= {passes * sample / (w['frames_per_segment'] - 1):.1f} "
                                    f"video-s) of the workload per step, oracle port of the reference (fp32 torch, "
@@ -278,6 +340,13 @@ def main():
     ap.add_argument("--num-text", type=int, default=0, help="prompt tokens T shared by all rows (text_input mode; default 0 = north-star)")
     ap.add_argument("--gather-batches", type=int, default=2, help="row batches per step at N > 1 (comm/compute overlap)")
     ap.add_argument("--no-multicast", action="store_true", help="N > 1: use the NCCL all-gather instead of multicast stores")
+    ap.add_argument("--entry", default="auto", choices=["auto", "frames", "tokens"],
+                    help="frames: from the towers' outputs through tdc_compress_frames (default where the workload has "
+                         "d_enc == d_out); tokens: Q-Former + vision_proj on already projected tokens (round 1's line)")
+    ap.add_argument("--no-fold", action="store_true", help="frames entry: run every projection as the reference orders them")
+    ap.add_argument("--unfolded-steps", type=int, default=3, help="frames entry, N = 1: timed steps of the fold = 0 sub-record")
+    ap.add_argument("--no-qformer-only", action="store_true", help="skip the round-1 style sub-record (N = 1 only)")
+    ap.add_argument("--e2e-chunks-per-batch", type=int, default=300, help="chunks per H2D range of compress_frames_host")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.segments:
@@ -286,6 +355,11 @@ def main():
     if args.num_query:
         w["num_query"] = args.num_query
     w.setdefault("projector", "vision_proj")
+    frames_ok = w["projector"] == "vision_proj" and w["d_enc"] == w["d_out"] and w["kv_tokens"] == 144 + 12 + w["audio_tokens"]
+    if args.entry == "frames" and not frames_ok:
+        raise SystemExit(f"workload {args.workload} has no frames entry (needs d_enc == d_out and L = 156 + audio)")
+    w["entry"] = "frames" if (args.entry == "frames" or (args.entry == "auto" and frames_ok)) else "tokens"
+    w["d_frame_in"] = 1024
     if args.impl == "reference":
         return run_reference_arm(args, w)
 
@@ -305,6 +379,329 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    ctx = dict(world=world, rank=rank, local_rank=local_rank, dev=dev, dist=dist)
+    if w["entry"] == "frames":
+        line = bench_frames(args, w, ctx)
+        if world == 1 and not args.no_qformer_only:
+            torch.cuda.empty_cache()
+            sub_args = argparse.Namespace(**vars(args))
+            sub_args.no_e2e, sub_args.no_cpu_baseline, sub_args.parity_rows = True, True, 0
+            q = bench_tokens(sub_args, dict(w, entry="tokens"), ctx)
+            line["qformer_only"] = {
+                "desc": "round 1's line: Q-Former + vision_proj + L2-normalise on already projected tokens "
+                        "[rows, 206, 3584] resident in HBM (tdc_compress)",
+                "value": q["value"], "unit": q["unit"], "ms_per_step": q["ms_per_step"], "steps": q["steps"],
+                "roofline": q["roofline"], "path": q["path"], "gpu_launches": q["gpu_launches"]}
+    else:
+        line = bench_tokens(args, w, ctx)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_frames(args, w, ctx):
+    """The path from the towers' outputs (tdc_compress_frames).  Returns the JSON line (rank 0; None elsewhere)."""
+    from tdc_video_b200 import QFormerEngine
+    world, rank, local_rank, dev, dist = ctx["world"], ctx["rank"], ctx["local_rank"], ctx["dev"], ctx["dist"]
+    geom, sd, rows = build_problem(w, 1234)
+    L, K, d, S, T, F_ = w["kv_tokens"], w["num_query"], w["d_enc"], w["segments"], w["num_text"], w["frames_per_segment"]
+    Ta, d_in = w["audio_tokens"], w["d_frame_in"]
+    fold = not args.no_fold
+    eng = QFormerEngine(d_enc=d, d_out=d, vocab=30522 if T else 0, device=dev, gemm_cta_group=args.cta_group,
+                        d_frame_in=d_in, d_audio=768 if Ta else 0)
+    eng.load_weights(sd)
+    n_frames = S * F_
+
+    # ---- synthetic tower outputs, generated on the device (8e9 normals are too slow on the host), copied to pinned
+    # HOST memory — the host copy is the source of truth: the resident tensors are uploaded from it and the e2e leg
+    # streams it every step
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pinned = not args.no_e2e
+
+    def host_empty(shape):
+        nonlocal pinned
+        if pinned:
+            try:
+                return torch.empty(shape, dtype=torch.bfloat16, pin_memory=True)
+            except RuntimeError as e:
+                print(f"[bench] rank {rank}: pinned allocation failed ({e}); using pageable host memory", file=sys.stderr)
+                pinned = False
+        return torch.empty(shape, dtype=torch.bfloat16)
+
+    frames_host = host_empty((n_frames, 144, d_in))
+    audio_host = host_empty((n_frames, Ta, 768)) if Ta else None
+    for f0 in range(0, n_frames, 2048):
+        f1 = min(n_frames, f0 + 2048)
+        frames_host[f0:f1].copy_(torch.randn((f1 - f0, 144, d_in), generator=g, device=dev).to(torch.bfloat16))
+        if Ta:
+            audio_host[f0:f1].copy_((torch.randn((f1 - f0, Ta, 768), generator=g, device=dev) * 0.5).to(torch.bfloat16))
+    frames_dev = frames_host.to(dev)
+    audio_dev = audio_host.to(dev) if Ta else None
+    ids_dev = None
+    if T > 0:   # one BERT-tokenised prompt per video, shared by every row (cambrian_arch.py:1532, 1643-1644)
+        ids_dev = torch.randint(1000, 30000, (1, T), generator=torch.Generator().manual_seed(7)).to(dev)
+
+    # ---- integer plan: every segment is one chunk of F frames, frame 0 the key frame (cambrian_arch.py:1603-1628)
+    chunk_start = np.arange(S, dtype=np.int64) * F_
+    chunk_len = np.full(S, F_, dtype=np.int64)
+
+    def plan_range(c0, c1):
+        """index tensors of chunks [c0, c1) — frame indices are global, chunk ids relative to the range"""
+        st = torch.from_numpy(chunk_start[c0:c1].astype(np.int32)).to(dev)
+        rf = (st[:, None] + torch.arange(1, F_, device=dev, dtype=torch.int32)[None, :]).reshape(-1).contiguous()
+        rc = torch.arange(c1 - c0, device=dev, dtype=torch.int32).repeat_interleave(F_ - 1)
+        return st, rf, rc
+
+    static_out = torch.empty((S, 144 + 12 + Ta, d), dtype=torch.bfloat16, device=dev)   # key frames pass through
+    nb = max(1, args.gather_batches) if world > 1 else 1
+    cb = [(S * b // nb, S * (b + 1) // nb) for b in range(nb)]
+    plans = [plan_range(c0, c1) for c0, c1 in cb]
+    full_plan = plan_range(0, S)
+    mcast, exchange = None, "none (1 GPU)"
+    gathered = None
+    if world > 1:
+        exchange = "NCCL all-gather of compressed tokens"
+        if not args.no_multicast:
+            try:
+                from tdc_video_b200.dist import MulticastGather
+                mcast = MulticastGather(rows, (K, d), torch.bfloat16, dev)
+                exchange = "NVSwitch multicast stores (multimem.st) from the final kernel + device barrier"
+            except Exception as e:  # transport fallback only; compute path is identical
+                if rank == 0:
+                    print(f"[bench] symmetric-memory multicast unavailable ({type(e).__name__}: {e}); using NCCL",
+                          file=sys.stderr)
+        if mcast is None:
+            gathered = torch.empty((world, rows, K, d), dtype=torch.bfloat16, device=dev)
+
+    def compute_range(plan, c0, c1, use_fold=True, mc_ptr=None, want_static=True):
+        st, rf, rc = plan
+        so, out = eng.compress_frames(frames_dev, st, rf, rc, audio=audio_dev, input_ids=ids_dev, num_query=K,
+                                      fold=use_fold, want_static=want_static, out_dtype=torch.bfloat16,
+                                      multicast_ptr=mc_ptr)
+        if want_static:
+            static_out[c0:c1].copy_(so)
+        return out
+
+    def make_step(chunks, plans_, mc, gath, chunk0=0, use_fold=True):
+        """step over the chunk ranges `chunks` (relative to chunk0 for the output slots)"""
+        def step():
+            if world == 1:
+                return compute_range(plans_[0], chunks[0][0], chunks[0][1], use_fold)
+            if mc is not None:
+                # all-gather fused into the producing kernel: the L2-normalise kernel stores every row through the
+                # multicast mapping, so all ranks receive it while the kernel runs
+                for (c0, c1), pl in zip(chunks, plans_):
+                    compute_range(pl, c0, c1, use_fold, mc_ptr=mc.slot_ptr((c0 - chunk0) * (F_ - 1)))
+                mc.barrier()
+                return mc.gathered
+            works = []
+            for (c0, c1), pl in zip(chunks, plans_):
+                out = compute_range(pl, c0, c1, use_fold)
+                r0, r1 = (c0 - chunk0) * (F_ - 1), (c1 - chunk0) * (F_ - 1)
+                works.append(dist.all_gather([gath[w_, r0:r1] for w_ in range(world)], out, async_op=True))
+            for wk in works:
+                wk.wait()
+            return gath.view(-1, K, d)
+        return step
+
+    step = make_step(cb, plans, mcast, gathered, 0, fold)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, n, warm=2):
+        for _ in range(warm):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        barrier()
+        tt = torch.tensor([a.elapsed_time(b) / n], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    assert torch.isfinite(out[:8].float()).all()
+    eng.set_profiling(True)
+    eng.reset_profile()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    prof = eng.profile()
+    eng.set_profiling(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    mine = torch.tensor([ms / args.steps, sum(v["ms"] for v in prof.values()) / args.steps], dtype=torch.float64, device=dev)
+    per_rank = [mine.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_gather(per_rank, mine)
+    per_rank = {"ms_per_step": [round(float(x[0]), 2) for x in per_rank],
+                "kernel_ms_per_step": [round(float(x[1]), 2) for x in per_rank]}
+    ms_step = float(t.item()) / args.steps
+    value = world * S / (ms_step * 1e-3)
+
+    # ---- N > 1: the exchange verifies itself, then ONE video sharded over the N GPUs (strong scaling)
+    exchange_check, strong = None, None
+    if world > 1:
+        final = step()
+        barrier()
+        local_all = compute_range(full_plan, 0, S, fold, want_static=False)
+        ref_gather = torch.empty((world * rows, K, d), dtype=torch.bfloat16, device=dev)
+        dist.all_gather_into_tensor(ref_gather, local_all.contiguous())
+        flag = torch.tensor([int(torch.equal(final.reshape(world * rows, K, d), ref_gather))], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        exchange_check = bool(flag.item())
+        del ref_gather, local_all, final
+
+        S_s = S // world                        # this rank's contiguous range of video-seconds of THE video
+        lo = rank * S_s
+        sb = [(lo + S_s * b // nb, lo + S_s * (b + 1) // nb) for b in range(nb)]
+        mc_s, gath_s = None, None
+        if mcast is not None:
+            from tdc_video_b200.dist import MulticastGather
+            mc_s = MulticastGather(S_s * (F_ - 1), (K, d), torch.bfloat16, dev)
+        else:
+            gath_s = torch.empty((world, S_s * (F_ - 1), K, d), dtype=torch.bfloat16, device=dev)
+        strong_step = make_step(sb, [plan_range(c0, c1) for c0, c1 in sb], mc_s, gath_s, lo, fold)
+        strong_ms = timed(strong_step, args.strong_steps)
+        n1_ms = timed(lambda: compute_range(full_plan, 0, S, fold), max(2, args.strong_steps // 2))
+        mine_s = compute_range(plan_range(lo, lo + S_s), lo, lo + S_s, fold, want_static=False)
+        got = strong_step().reshape(world, S_s * (F_ - 1), K, d)[rank]
+        flag = torch.tensor([int(torch.equal(got, mine_s))], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        strong = {"segments_total": S, "segments_per_gpu": S_s, "rows_per_gpu": S_s * (F_ - 1), "ms_per_step": strong_ms,
+                  "value": S / (strong_ms * 1e-3), "unit": "video-s/s", "one_gpu_ms_per_step": n1_ms,
+                  "speedup_vs_n1": n1_ms / strong_ms, "steps": args.strong_steps, "exchange": exchange,
+                  "own_rows_match": bool(flag.item()),
+                  "limiter": "per-GPU step = compute of S/N segments + the device barrier that closes the multicast "
+                             "exchange (~1-2 ms); every GPU is power-capped and the step follows the slowest one"}
+        del mc_s, gath_s
+
+    # ---- the same step with every projection as the reference orders it (no weight folding)
+    unfolded = None
+    if world == 1 and args.unfolded_steps > 0 and fold:
+        u_ms = timed(make_step(cb, plans, None, None, 0, False), args.unfolded_steps, warm=1)
+        unfolded = {"ms_per_step": u_ms, "value": S / (u_ms * 1e-3), "unit": "video-s/s", "steps": args.unfolded_steps,
+                    "desc": "fold = 0: mm_projector.2 and audio_proj run on every frame, K/V from the d_llm-wide tokens"}
+
+    # ---- end to end: the towers' outputs in pinned host memory, compressed tokens back in host memory
+    e2e = None
+    if not args.no_e2e:
+        out_host = torch.empty((rows, K, d), dtype=torch.bfloat16, pin_memory=pinned)
+        kw = dict(input_ids=None if ids_dev is None else ids_dev.cpu(), num_query=K, fold=fold, static_out=static_out,
+                  chunks_per_batch=args.e2e_chunks_per_batch)
+        if world > 1:
+            kw["out_device"] = torch.empty((rows, K, d), dtype=torch.bfloat16, device=dev)
+            if gathered is None:
+                gathered = torch.empty((world, rows, K, d), dtype=torch.bfloat16, device=dev)
+
+        def e2e_step():
+            eng.compress_frames_host(frames_host, audio_host, chunk_start, chunk_len, out_host, **kw)
+            if world > 1:   # (the result is read back to the host per range anyway: plain NCCL exchange here)
+                dist.all_gather_into_tensor(gathered.view(world * rows, K, d), kw["out_device"])
+        e2e_ms = timed(e2e_step, args.e2e_steps, warm=1)
+        # the streamed result equals the resident one
+        same = bool(torch.equal(out_host[:64].to(dev), compute_range(plan_range(0, 64 // (F_ - 1) + 1), 0,
+                                                                     64 // (F_ - 1) + 1, fold, want_static=False)[:64]))
+        h2d = frames_host.numel() * 2 + (audio_host.numel() * 2 if Ta else 0) + S * 4 + 2 * rows * 4
+        e2e = {"value": world * S / (e2e_ms * 1e-3), "unit": "video-s/s", "ms_per_step": e2e_ms, "steps": args.e2e_steps,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host.numel() * 2,
+               "host_memory": "pinned" if pinned else "pageable", "matches_resident": same,
+               "api": "QFormerEngine.compress_frames_host (tdc_compress_frames per range of chunks; H2D of the "
+                      "towers' outputs / compute / D2H of the compressed tokens on 3 streams)"}
+
+    if rank != 0:
+        return None
+
+    peaks = measured_peaks()
+    model_s, exec_s, kv_exec_s = frames_flops(w, 144, d_in, 768)
+    if not fold:
+        f_row, f_row_kv = flops_per_row(L, d, K, T, d)
+        exec_s = model_s
+        kv_exec_s = (F_ - 1) * 2 * (144 + Ta) * d * 2 * H * N_CROSS
+    kv_ms, kv_n = prof["kv_gemm"]["ms"], prof["kv_gemm"]["launches"]
+    kv_flops_total = kv_exec_s * S * args.steps
+    kv_achieved = kv_flops_total / (kv_ms * 1e-3) / 1e12 if kv_ms > 0 else None
+    line = {
+        "metric": "video_seconds_per_sec", "value": value, "unit": "video-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["label"], "entry": "frames (tdc_compress_frames)",
+                   "boundary": "tower features [frames, 144, 1024] + audio tokens [frames, 50, 768] -> mm_projector, "
+                               "image_newline, audio_proj, query build, Q-Former, vision_proj + L2-normalise -> "
+                               "key-frame tokens [chunks, 206, d] + compressed tokens [rows, K, d]",
+                   "segments_per_gpu": S, "frames_per_gpu": n_frames, "rows_per_gpu": rows, "kv_tokens": L, "d_enc": d,
+                   "d_out": d, "d_frame_in": d_in, "num_query": K, "num_text": T, "fold": fold,
+                   "parallelism": f"dp{world} (video-second ranges per GPU)", "exchange": exchange,
+                   "l2": f"inputs {(frames_dev.numel() + (audio_dev.numel() if Ta else 0)) * 2 / 1e9:.1f} GB per GPU "
+                         f">> 126 MB L2 (no flush needed)",
+                   "accumulate": "fp32 (TMEM), LN/softmax/residual fp32"},
+        "clocks": clocks, "exchange_check": exchange_check, "strong": strong, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": {"kernel": "tdc_gemm_kernel (cross-attn K/V projection of all 6 layers, N=9216: visual tokens "
+                               "K=3584 + audio tokens K=768 per row batch)",
+                     "bound": "tensor", "achieved": kv_achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": (kv_achieved / peaks["tflops_sustained"]) if kv_achieved else None, "traffic": None,
+                     "flops": "EXECUTED by these launches (folded weights): rows x (2*144*3584 + 2*50*768) x 9216",
+                     "peak_source": peaks["source"] + " bf16_tflops_sustained", "launches": kv_n,
+                     "avg_launch_ms": kv_ms / max(kv_n, 1), "share_of_step": kv_ms / (ms_step * args.steps)},
+        "path": {"model_tflop_per_step": model_s * S / 1e12, "executed_tflop_per_step": exec_s * S / 1e12,
+                 "model_tflops": model_s * S / (ms_step * 1e-3) / 1e12,
+                 "executed_tflops": exec_s * S / (ms_step * 1e-3) / 1e12,
+                 "executed_frac_of_sustained_peak": exec_s * S / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"],
+                 "model_frac_of_sustained_peak": model_s * S / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"],
+                 "gflop_per_video_second": {"model": model_s / 1e9, "executed": exec_s / 1e9},
+                 "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}},
+        "ranks": per_rank, "unfolded": unfolded,
+    }
+    if args.parity_rows > 0:
+        # the timed workload's own first chunks against the CPU oracle (checker only)
+        from oracle import frames_oracle, qformer_oracle as oracle
+        n_c = max(1, args.parity_rows // (F_ - 1))
+        got = compute_range(plan_range(0, n_c), 0, n_c, fold, want_static=False).float().cpu()
+        sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
+        ref_st, ref = frames_oracle.frames_stage(sd_t, geom, frames_host[:n_c * F_].float(),
+                                                 None if not Ta else audio_host[:n_c * F_].float(), chunk_start[:n_c],
+                                                 chunk_len[:n_c], K, None if ids_dev is None else ids_dev.cpu())
+        pm = oracle.parity_metrics(got, ref)
+        ps = oracle.parity_metrics(static_out[:n_c].float().cpu(), ref_st)
+        okf = lambda m_: bool(m_["min_cos"] >= 0.999 and m_["max_abs_over_max_ref"] <= 2e-2 and m_["max_tok_rel_l2"] <= 2e-2)
+        line["parity_sample"] = dict(chunks=n_c, rows=int(got.shape[0]), num_query=K, **pm, ok=okf(pm),
+                                     key_frames=dict(**ps, ok=okf(ps)))
+    if not args.no_cpu_baseline:
+        passes = args.cpu_passes or 12
+        v, dt, cores = cpu_baseline(geom, sd, w, args.cpu_sample_rows, 99, passes)
+        line["cpu_baseline"] = {"value": v, "unit": "video-s/s", "cores": cores, "kind": "port",
+                                "sample": f"{passes} x {args.cpu_sample_rows // (F_ - 1)} video-seconds of the same "
+                                          f"workload in {dt:.1f} s (oracle port of the reference from the towers' "
+                                          f"outputs, fp32 torch, one batched call per pass)"}
+    return line
+
+
+def bench_tokens(args, w, ctx):
+    """Q-Former + vision_proj + L2-normalise on already projected frame tokens (tdc_compress): round 1's line and
+    the variant workloads.  Returns the JSON line (rank 0; None elsewhere)."""
+    from tdc_video_b200 import QFormerEngine
+    world, rank, local_rank, dev, dist = ctx["world"], ctx["rank"], ctx["local_rank"], ctx["dev"], ctx["dist"]
     geom, sd, rows = build_problem(w, 1234)
     L, K, d_enc, d_out = w["kv_tokens"], w["num_query"], w["d_enc"], w["d_out"]
     S = w["segments"]
@@ -331,22 +728,26 @@ def main():
     #  source of truth: the resident tensor is uploaded from it, and e2e streams it every step)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     pinned = not args.no_e2e
-    try:
-        enc_host = torch.empty((rows, L, d_enc), dtype=torch.bfloat16, pin_memory=pinned)
-    except RuntimeError as e:  # e.g. cudaHostAlloc limit on a box with many ranks: pageable staging instead
-        print(f"[bench] rank {rank}: pinned allocation failed ({e}); using pageable host memory", file=sys.stderr)
-        pinned = False
-        enc_host = torch.empty((rows, L, d_enc), dtype=torch.bfloat16)
+    enc_host = None
+    if not args.no_e2e:
+        try:
+            enc_host = torch.empty((rows, L, d_enc), dtype=torch.bfloat16, pin_memory=True)
+        except RuntimeError as e:  # e.g. cudaHostAlloc limit on a box with many ranks: pageable staging instead
+            print(f"[bench] rank {rank}: pinned allocation failed ({e}); using pageable host memory", file=sys.stderr)
+            pinned = False
+            enc_host = torch.empty((rows, L, d_enc), dtype=torch.bfloat16)
+    enc = torch.empty((rows, L, d_enc), dtype=torch.bfloat16, device=dev)
     chunk = 1024
     for r0 in range(0, rows, chunk):
         r1 = min(rows, r0 + chunk)
         blk = torch.randn((r1 - r0, L, d_enc), generator=g, device=dev)
         blk[:, L - w["audio_tokens"]:] *= 0.5
-        enc_host[r0:r1].copy_(blk.to(torch.bfloat16))
+        enc[r0:r1].copy_(blk.to(torch.bfloat16))
+        if enc_host is not None:
+            enc_host[r0:r1].copy_(enc[r0:r1])
     del blk
     q_sets = torch.randn((S, K, H), generator=g, device=dev).cpu()    # one query set per segment
     query_set = (torch.arange(rows) // (w["frames_per_segment"] - 1)).to(torch.int32)
-    enc = enc_host.to(dev)
     q_dev, qs_dev = q_sets.to(dev), query_set.to(dev)
     ids_dev = ts_dev = None
     if T > 0:   # one BERT-tokenised prompt per video, shared by every row (cambrian_arch.py:1532, 1643-1644)
@@ -537,9 +938,7 @@ def main():
                "api": "QFormerEngine.compress_host (tdc_compress per row batch, H2D / compute / D2H on 3 streams)"}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     peaks = measured_peaks()
     f_row, f_row_kv = flops_per_row(L, d_enc, K, T, d_out, w["projector"])
@@ -583,7 +982,7 @@ def main():
         got = compute(enc[:n_chk], qs_dev[:n_chk], None if ts_dev is None else ts_dev[:n_chk]).float().cpu()
         sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
         ids_chk = None if ids_dev is None else ids_dev.cpu().expand(n_chk, -1)
-        ref = oracle.compress(sd_t, geom, q_sets[query_set[:n_chk].long()], enc_host[:n_chk].float(), ids_chk)
+        ref = oracle.compress(sd_t, geom, q_sets[query_set[:n_chk].long()], enc[:n_chk].float().cpu(), ids_chk)
         pm = oracle.parity_metrics(got, ref)
         line["parity_sample"] = dict(rows=n_chk, num_query=K, **pm,
                                      ok=bool(pm["min_cos"] >= 0.999 and pm["max_abs_over_max_ref"] <= 2e-2
@@ -598,9 +997,7 @@ def main():
             line["cpu_baseline"]["reference_batching"] = {
                 "rows_per_call": 7, "unit": "video-s/s",
                 "value": cpu_baseline_reference_batching(geom, sd, w, args.cpu_sample_rows, 99)}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":

@@ -94,32 +94,13 @@ def _full_problem(seed, n_frames, chunk, audio=True, T=0, d=3584, d_in=1024):
 
 
 def _oracle_frames(sd, geom, frames, aud, sizes, K, ids=None):
-    """CPU oracle of the frames stage on bf16-rounded inputs: (static tokens per chunk, compressed rows)."""
-    t = lambda k: torch.from_numpy(sd[k])
+    """CPU oracle of the frames stage on the bf16-rounded inputs the GPU sees."""
+    from oracle import frames_oracle
+    from tdc_video_b200.compressor import plan_chunks
+    p = plan_chunks(sizes, True)
     x = torch.from_numpy(frames).bfloat16().float()
-    xv = oracle.gelu_mlp(t("mm_projector.0.weight"), t("mm_projector.0.bias"), t("mm_projector.2.weight"),
-                         t("mm_projector.2.bias"), x)
-    n = xv.shape[0]
-    nl = t("image_newline").view(1, 1, 1, -1).expand(n, 12, 1, -1)
-    fr = torch.cat([xv.view(n, 12, 12, -1), nl], dim=2).flatten(1, 2)                      # [n, 156, d]
-    full = fr
-    if aud is not None:
-        a = torch.from_numpy(aud).bfloat16().float()
-        full = torch.cat([fr, torch.nn.functional.linear(a, t("audio_proj.weight"), t("audio_proj.bias"))], dim=1)
-    statics, comps = [], []
-    f0 = 0
-    sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
-    for s in sizes:
-        for c0 in range(f0, f0 + s, 8):
-            c1 = min(c0 + 8, f0 + s)
-            statics.append(full[c0])
-            if c1 - c0 > 1:
-                q = oracle.avg_pool_queries(fr[c0][None], K)
-                q = torch.nn.functional.linear(q, t("query_proj.weight"), t("query_proj.bias")).expand(c1 - c0 - 1, -1, -1)
-                i = None if ids is None else ids.expand(c1 - c0 - 1, -1)
-                comps.append(oracle.compress(sd_t, geom, q, full[c0 + 1:c1], i))
-        f0 += s
-    return torch.stack(statics), torch.cat(comps)
+    a = None if aud is None else torch.from_numpy(aud).bfloat16().float()
+    return frames_oracle.frames_stage(sd, geom, x, a, p.static_frames, p.chunk_len, K, ids)
 
 
 def _engine(geom, sd, d_in, audio, T=0):
