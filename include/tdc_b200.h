@@ -175,6 +175,10 @@ typedef struct tdc_frames_args {
   int32_t fold;
   int32_t multicast;             /* 1: `out` is an NVSwitch multicast address (see tdc_compress_multicast) */
   int32_t out_dtype;             /* dtype of out and static_out */
+  int32_t no_layer0_dedup;       /* 0 (default): all rows of a chunk share their queries and the prompt
+                                  * (cambrian_arch.py:1629-1646), so embeddings + the self-attention block of layer 0
+                                  * are computed once per chunk and broadcast to its rows (bit-identical);
+                                  * 1: computed per row */
   void* static_out;              /* [n_chunks, side*(side+1) + Ta, d_out] the key frames as they pass through, or NULL */
   void* out;                     /* [rows, K, d_out] compressed tokens */
 } tdc_frames_args;

@@ -51,6 +51,7 @@ class TdcFramesArgs(C.Structure):
         ("n_frames", C.c_int32), ("n_chunks", C.c_int32), ("rows", C.c_int32), ("visual_tokens", C.c_int32),
         ("audio_tokens", C.c_int32), ("num_query", C.c_int32), ("num_text", C.c_int32),
         ("learned_queries", C.c_int32), ("fold", C.c_int32), ("multicast", C.c_int32), ("out_dtype", C.c_int32),
+        ("no_layer0_dedup", C.c_int32),
         ("static_out", C.c_void_p), ("out", C.c_void_p),
     ]
 

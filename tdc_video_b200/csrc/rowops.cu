@@ -11,7 +11,7 @@ namespace tdc {
 
 namespace {
 
-constexpr int kMaxVec = 8;  // float4 per lane cached in registers: width <= 1024
+constexpr int kMaxVec = 12;  // float4 per lane cached in registers: width <= 1536 (Whisper-large features are 1280 wide)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -169,6 +169,33 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
   for (int j = lane; j < hidden / 4; j += 32) store4_from_f32(out, out_dtype, tok * (hidden / 4) + j, s[j]);
 }
 
+// h (slab layout of `rows` rows) <- sets[set_map[r]] (set-major [set][K + T][hidden], fp32): the layer-0 state
+// computed once per (query set, prompt) broadcast to every row that shares it; also writes the bf16 copy.
+__global__ void __launch_bounds__(256) broadcast_sets_kernel(const float* __restrict__ sets,
+                                                             const int32_t* __restrict__ set_map, int rows,
+                                                             int num_query, int num_text, int hidden,
+                                                             float* __restrict__ h_f32,
+                                                             __nv_bfloat16* __restrict__ h_bf16) {
+  const int n = num_query + num_text;
+  const long long tok = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (tok >= static_cast<long long>(rows) * n) return;
+  const int lane = threadIdx.x & 31;
+  const int r = static_cast<int>(tok / n), i = static_cast<int>(tok % n);
+  const long long set = set_map ? set_map[r] : 0;
+  const float4* src = reinterpret_cast<const float4*>(sets + (set * n + i) * hidden);
+  const long long dst = (i < num_query) ? static_cast<long long>(r) * num_query + i
+                                        : static_cast<long long>(rows) * num_query +
+                                              static_cast<long long>(r) * num_text + (i - num_query);
+  for (int j = lane; j < hidden / 4; j += 32) {
+    const float4 v = __ldg(src + j);
+    reinterpret_cast<float4*>(h_f32 + dst * hidden)[j] = v;
+    uint2 raw;
+    raw.x = pack_bf16x2(v.x, v.y);
+    raw.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(h_bf16 + dst * hidden)[j] = raw;
+  }
+}
+
 // 16-byte store; kMulticast: `p` is an NVSwitch multicast address (all GPUs of the group receive the
 // bytes with one store — the all-gather of the compressed tokens rides on this kernel's output).
 template <bool kMulticast>
@@ -309,7 +336,7 @@ int layernorm_launch(const float* x, long long ldx, const float* resid, long lon
                      int width, cudaStream_t stream, const char** err, int resid_period) {
   if (rows <= 0) return TDC_OK;
   if (width % 4 != 0 || width > kMaxVec * 128 || ldx % 4 != 0 || ldy % 4 != 0 || ldr % 4 != 0) {
-    if (err) *err = "layernorm: width must be a multiple of 4 and <= 1024";
+    if (err) *err = "layernorm: width must be a multiple of 4 and <= 1536";
     return TDC_EINVAL;
   }
   layernorm_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(x, ldx, resid, ldr, gamma, beta, eps,
@@ -321,7 +348,7 @@ int layernorm_launch(const float* x, long long ldx, const float* resid, long lon
 int embed_layernorm_launch(const EmbedArgs& a, cudaStream_t stream, const char** err) {
   if (a.rows <= 0) return TDC_OK;
   if (a.hidden % 4 != 0 || a.hidden > kMaxVec * 128) {
-    if (err) *err = "embeddings: hidden must be a multiple of 4 and <= 1024";
+    if (err) *err = "embeddings: hidden must be a multiple of 4 and <= 1536";
     return TDC_EINVAL;
   }
   const long long toks = static_cast<long long>(a.rows) * (a.num_query + a.num_text);
@@ -335,6 +362,15 @@ int gather_rows_launch(const float* h_f32, int hidden, int rows, int num_query, 
   if (toks <= 0) return TDC_OK;
   gather_rows_kernel<<<static_cast<unsigned>((toks + 7) / 8), 256, 0, stream>>>(h_f32, hidden, rows, num_query,
                                                                                 num_text, tokens_out, out, out_dtype);
+  return check_launch(err);
+}
+
+int broadcast_sets_launch(const float* sets, const int32_t* set_map, int rows, int num_query, int num_text, int hidden,
+                          float* h_f32, __nv_bfloat16* h_bf16, cudaStream_t stream, const char** err) {
+  const long long toks = static_cast<long long>(rows) * (num_query + num_text);
+  if (toks <= 0) return TDC_OK;
+  broadcast_sets_kernel<<<static_cast<unsigned>((toks + 7) / 8), 256, 0, stream>>>(sets, set_map, rows, num_query,
+                                                                                   num_text, hidden, h_f32, h_bf16);
   return check_launch(err);
 }
 

@@ -339,6 +339,11 @@ struct ForwardCall {
   void* out; int out_dtype;   // hidden [rows, K+T, H] or compressed [rows, K, d_out]
   bool compress;
   bool multicast = false;     // compress only: `out` is an NVSwitch multicast address
+  // layer-0 de-duplication (rows that share queries and prompt, cambrian_arch.py:1629-1646):
+  float* l0_out = nullptr;            // pre-pass: stop after the self-attention block of layer 0 and write the
+                                      // state of every "row" (= one per set) set-major [rows, K + T, hidden] fp32
+  const float* l0_sets = nullptr;     // main pass: start from these states instead of recomputing them per row
+  const int32_t* l0_map = nullptr;    // [rows] row -> set (NULL: set 0)
 };
 
 #define TDC_TRY(expr)                                         \
@@ -378,7 +383,11 @@ int qformer_layers(tdc_handle* h, const ForwardCall& f, long long row0, long lon
   const float scale_log2 = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(64)
 
   // embeddings + LayerNorm into the [query slab | text slab] layout
-  {
+  if (f.l0_sets != nullptr) {
+    KernelScope ks(h, TDC_K_ROWOPS, s);
+    TDC_TRY(broadcast_sets_launch(f.l0_sets, f.l0_map ? f.l0_map + row0 : nullptr, static_cast<int>(rows), K, T, H,
+                                  w.h_f32, w.h_bf16, s, &err));
+  } else {
     EmbedArgs e;
     const size_t qsz = f.query_dtype == TDC_F32 ? 4 : 2;
     e.query_embeds = f.query_set ? f.query_embeds
@@ -408,10 +417,12 @@ int qformer_layers(tdc_handle* h, const ForwardCall& f, long long row0, long lon
     // tdc_compress reads only the query tokens of the last layer (cambrian_arch.py:1665 `[:, :K]`): there the
     // text tokens still feed the queries' self-attention as keys / values, but their own attention output,
     // out-projection, LayerNorms and feed-forward are dead and are skipped (the query tokens' bits do not change).
-    const bool text_live = T > 0 && !(f.compress && l == c.layers - 1);
+    const bool text_live = T > 0 && !(f.compress && l == c.layers - 1 && f.l0_out == nullptr);
     const int nq_self = text_live ? n : K;
     const long long M_self = text_live ? MA : MQ;
     // ---- self-attention over all K+T tokens of the row
+    const bool self_done = (l == 0 && f.l0_sets != nullptr);   // layer 0's self block came from the per-set pre-pass
+    if (!self_done) {
     TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16, H, lw.w_qkv, H, lw.b_qkv, w.qkv, 3 * H, MA, 3 * H, H,
                  EPI_BIAS_BF16, &err));
     {
@@ -427,6 +438,13 @@ int qformer_layers(tdc_handle* h, const ForwardCall& f, long long row0, long lon
     }
     TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.ctx, H, lw.w_ao, H, lw.b_ao, w.pre, H, M_self, H, H, EPI_BIAS_F32, &err));
     TDC_TRY(ln(lw.ln_a_g, lw.ln_a_b, 0, M_self));
+    }
+    if (f.l0_out != nullptr) {   // pre-pass: the state after layer 0's self-attention block, one "row" per set
+      KernelScope ks(h, TDC_K_ROWOPS, s);
+      TDC_TRY(gather_rows_launch(w.h_f32, H, static_cast<int>(rows), K, T, n,
+                                 f.l0_out + static_cast<size_t>(row0) * n * H, TDC_F32, s, &err));
+      return TDC_OK;
+    }
 
     // ---- cross-attention: query tokens only
     if (lw.cross_index >= 0) {
@@ -560,7 +578,8 @@ struct FramesCall {
 struct FramesWorkspace {
   // whole call
   float* q_sets;       // [n_chunks, K, H] fp32 (Avg_pool queries, one set per chunk)
-  int32_t* zero_map;   // [rows] zeros: "every row uses set 0" (shared prompt / learned queries)
+  int32_t* zero_map;   // [max(rows, n_chunks)] zeros: "every row uses set 0" (shared prompt / learned queries)
+  float* l0_sets;      // [n_chunks, K + T, H] fp32: state after layer 0's self-attention block, one per chunk
   // per batch of nb items (nb key frames in the static pass, nb rows in the dynamic pass)
   __nv_bfloat16* fin;     // [nb*Tv, d_in]   gathered tower features
   __nv_bfloat16* pmid;    // [nb*Tv, d]      gelu(mm_projector.0)
@@ -580,7 +599,8 @@ FramesWorkspace carve_frames(const tdc_handle* h, uint8_t* base, long long n_chu
   Carver cv{base};
   FramesWorkspace w{};
   w.q_sets = cv.take<float>(static_cast<size_t>(n_chunks) * K * H);
-  w.zero_map = cv.take<int32_t>(static_cast<size_t>(rows));
+  w.zero_map = cv.take<int32_t>(static_cast<size_t>(std::max(rows, n_chunks)));
+  w.l0_sets = cv.take<float>(static_cast<size_t>(n_chunks) * (K + T) * H);
   w.fin = cv.take<__nv_bfloat16>(N * Tv * c.d_frame_in);
   w.pmid = cv.take<__nv_bfloat16>(N * Tv * D);
   w.xv = cv.take<__nv_bfloat16>(N * Tv * D);
@@ -956,7 +976,8 @@ int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* worksp
   if (a.rows == 0) return TDC_OK;
   // pass 2: dynamic frames
   const bool zero_map = fc.learned || fc.T > 0;
-  if (zero_map && cudaMemsetAsync(w.zero_map, 0, static_cast<size_t>(a.rows) * sizeof(int32_t), s) != cudaSuccess)
+  if (zero_map && cudaMemsetAsync(w.zero_map, 0, static_cast<size_t>(std::max(a.rows, a.n_chunks)) * sizeof(int32_t),
+                                  s) != cudaSuccess)
     return fail(h, TDC_ECUDA, "cudaMemsetAsync failed");
   ForwardCall f{};
   f.query_embeds = fc.learned ? h->query_tokens : w.q_sets;
@@ -967,6 +988,25 @@ int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* worksp
   f.enc = nullptr; f.enc_dtype = TDC_BF16; f.kv_len = nullptr;
   f.rows = a.rows; f.L = fc.Tv + fc.Ta + fc.side; f.K = fc.K; f.T = fc.T;
   f.out = a.out; f.out_dtype = a.out_dtype; f.compress = true; f.multicast = a.multicast != 0;
+  // layer-0 de-duplication: every row of a chunk has the same queries and the same prompt, hence the same state up
+  // to and including layer 0's self-attention block — compute it once per chunk (once in total for learned queries)
+  // and broadcast it.  Same kernels on the same values: bit-identical to the per-row computation.
+  if (!a.no_layer0_dedup && c.layers > 1) {
+    const long long n_sets = fc.learned ? 1 : a.n_chunks;
+    ForwardCall p = f;
+    p.rows = n_sets;
+    p.query_set = nullptr;            // "row" i of the pre-pass uses query set i
+    p.l0_out = w.l0_sets;
+    Workspace qw0{};
+    for (long long s0 = 0; s0 < n_sets; s0 += nb) {
+      const long long sb = std::min<long long>(nb, n_sets - s0);
+      qw0 = carve_workspace(h, w.qws, sb, 0, fc.K, fc.T, false, true);
+      const int rc = qformer_layers(h, p, s0, sb, qw0, KvView{}, nullptr, s);
+      if (rc != TDC_OK) return rc;
+    }
+    f.l0_sets = w.l0_sets;
+    f.l0_map = fc.learned ? nullptr : a.row_chunk;
+  }
   for (long long r0 = 0; r0 < a.rows; r0 += nb) {
     const int rc = frames_dynamic_batch(h, fc, f, w, r0, std::min<long long>(nb, a.rows - r0), s);
     if (rc != TDC_OK) return rc;

@@ -71,6 +71,10 @@ int embed_layernorm_launch(const EmbedArgs& a, cudaStream_t stream, const char**
 int gather_rows_launch(const float* h_f32, int hidden, int rows, int num_query, int num_text, int tokens_out,
                        void* out, int out_dtype, cudaStream_t stream, const char** err);
 
+// h (slab layout) <- sets[set_map[r]] (set-major [set][K + T][hidden] fp32; set_map NULL = set 0 for every row)
+int broadcast_sets_launch(const float* sets, const int32_t* set_map, int rows, int num_query, int num_text, int hidden,
+                          float* h_f32, __nv_bfloat16* h_bf16, cudaStream_t stream, const char** err);
+
 // F.normalize(x, dim=-1) (eps 1e-12; tdc/cambrian_arch.py:1664-1667): x fp32 [rows, width] -> out_dtype.
 // multicast: `out` is an NVSwitch multicast address (multimem.st): every GPU of the group gets the rows.
 int l2_normalize_launch(const float* x, long long ldx, void* out, int out_dtype, long long rows, int width,

@@ -242,7 +242,7 @@ class QFormerEngine:
                         row_chunk: torch.Tensor, *, audio: Optional[torch.Tensor] = None,
                         input_ids: Optional[torch.Tensor] = None, num_query: int = 16, learned_queries: bool = False,
                         fold: bool = True, want_static: bool = True, out_dtype=torch.bfloat16,
-                        multicast_ptr: Optional[int] = None):
+                        multicast_ptr: Optional[int] = None, layer0_dedup: bool = True):
         """The TDC stage from the towers' outputs (tdc_compress_frames): mm_projector, image_newline, audio_proj,
         query build, Q-Former, vision_proj + L2-normalise for all chunks of a video in one call.
 
@@ -280,7 +280,7 @@ class QFormerEngine:
         a = TdcFramesArgs(frames.data_ptr(), None if audio is None else audio.data_ptr(), sf.data_ptr(), rf.data_ptr(),
                           rc_.data_ptr(), None if ids is None else ids.data_ptr(), n_frames, C_, R, Tv, Ta, num_query,
                           T, int(learned_queries), int(fold), int(multicast_ptr is not None), _DTYPES[out_dtype],
-                          None if static_out is None else static_out.data_ptr(),
+                          int(not layer0_dedup), None if static_out is None else static_out.data_ptr(),
                           int(multicast_ptr) if multicast_ptr is not None else out.data_ptr())
         with torch.cuda.device(dev):
             rc = self.lib.tdc_compress_frames(self._h, C.byref(a), _ptr(ws), ws.numel(), _stream(dev))

@@ -149,6 +149,11 @@ def test_frames_entry_text_and_ragged_chunks():
     assert tuple(st.shape) == (3, 156, 3584)
     _ok(st, ref_st, "static text")
     _ok(comp, ref_comp, "compressed text")
+    # layer-0 de-duplication (embeddings + self-attention block of layer 0 once per chunk, incl. the prompt tokens)
+    # does not change a bit
+    st2, comp2 = eng.compress_frames(torch.from_numpy(frames).cuda().bfloat16(), sf, rf, rc, input_ids=ids.cuda(),
+                                     out_dtype=torch.float32, layer0_dedup=False)
+    assert torch.equal(comp, comp2) and torch.equal(st, st2)
 
 
 def test_frames_small_workspace_and_host_streaming_give_the_same_bits():
@@ -159,6 +164,8 @@ def test_frames_small_workspace_and_host_streaming_give_the_same_bits():
     p, sf, rf, rc = _plan(sizes)
     f_dev, a_dev = torch.from_numpy(frames).cuda().bfloat16(), torch.from_numpy(aud).cuda().bfloat16()
     st, comp = eng.compress_frames(f_dev, sf, rf, rc, audio=a_dev)
+    _, comp_nd = eng.compress_frames(f_dev, sf, rf, rc, audio=a_dev, layer0_dedup=False, want_static=False)
+    assert torch.equal(comp, comp_nd)               # layer-0 de-duplication is bit-identical
     small = int(eng.lib.tdc_frames_workspace_bytes(eng._h, p.num_chunks, p.num_rows, 5, 144, 50, 16, 0))
     eng._ws, eng.max_workspace_bytes = None, small
     st2, comp2 = eng.compress_frames(f_dev, sf, rf, rc, audio=a_dev)

@@ -286,6 +286,31 @@ def test_speech_qformer_geometry():
     _metrics_ok(out, ref, "speech qformer geometry")
 
 
+def test_speech_qformer_module_matches_oracle():
+    """The drop-in for audio_encoder.py:10-24, 75-116: LayerNorms, pad + concat, 17-frame windows, the 2-layer
+    cross-every-layer Q-Former with ONE query, speech_llama_proj — Whisper-large (1280) + BEATs (768) widths."""
+    from oracle import speech_oracle
+    from tdc_video_b200.speech import TDCSpeechQFormer
+    mod = TDCSpeechQFormer(1280, 768, llama_hidden_size=512, vocab_size=32)
+    _randomize(mod, 21)
+    with torch.no_grad():
+        for ln in (mod.ln_speech, mod.ln_audio):
+            ln.weight.add_(1.0)
+    mod = mod.cuda().eval()
+    sd = {}
+    for k, v in mod.state_dict().items():
+        k = k[len("speech_Qformer.bert."):] if k.startswith("speech_Qformer.bert.") else k
+        sd[k] = v.detach().cpu()
+    assert "encoder.layer.1.crossattention.self.key.weight" in sd and sd["speech_query_tokens"].shape == (1, 1, 768)
+    B, T = 2, 100                                  # 100 frames -> 5 windows of 17 (the tail is dropped by unfold)
+    speech = torch.randn(B, T, 1280)
+    audio = torch.randn(B, T - 4, 768)             # shorter BEATs track: zero-padded (:83-84)
+    y, atts = mod.encode_auditory_feature(speech.cuda(), audio.cuda())
+    ref = speech_oracle.encode_auditory_feature(sd, _geom_of(mod.speech_Qformer.config, 0), speech, audio)
+    assert y.shape == ref.shape == (B, 5, 512) and atts.shape == (B, 5) and bool(atts.all())
+    _metrics_ok(y, ref, "speech qformer module")
+
+
 @pytest.mark.parametrize("pattern", ["every_second", "sparse"])
 def test_audio_pooling_matches_oracle(pattern):
     """tdc_video_b200.audio.pool_audio_per_frame (tdc_avg_pool_tokens kernel) vs the restated
