@@ -197,6 +197,14 @@ int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* worksp
 int tdc_linear(const void* x, const void* w, const float* bias, void* y, int32_t m, int32_t n, int32_t k,
                int32_t out_dtype, int32_t gelu, int32_t cta_group, tdc_stream_t stream);
 
+/* replaces: BertSelfOutput / BertOutput forward — LayerNorm(dense(x) + input_tensor), tdc/Qformer.py:285-289, 371-375 —
+ * as ONE kernel: y = LayerNorm(x[m, k] . w[n, k]^T + bias + resid) * gamma + beta, written as fp32 and as bf16.
+ * x, w bf16; bias, resid [m, n], gamma, beta fp32; resid may alias y_f32; n <= 768 (a thread-block cluster of
+ * ceil(n / 256) CTAs holds one LayerNorm row; row statistics are exchanged through distributed shared memory). */
+int tdc_linear_layernorm(const void* x, const void* w, const float* bias, const float* resid, const float* gamma,
+                         const float* beta, float eps, float* y_f32, void* y_bf16, int32_t m, int32_t n, int32_t k,
+                         tdc_stream_t stream);
+
 /* replaces: mm_projector = Linear -> GELU(erf) -> Linear (cambrian_arch.py:65-69,1149-1150;
  * tdc/multimodal_projector/builder.py:40-47).  x [m, d_in] bf16, w0 [d_mid, d_in], w1 [d_out, d_mid] bf16,
  * biases fp32, mid = caller scratch [m, d_mid] bf16, y [m, d_out] bf16. */

@@ -24,7 +24,7 @@ KERNEL_CLASS_NAMES = ["kv_gemm", "query_gemm", "attention", "rowops", "frontend"
 EXPORTED_SYMBOLS = [
     "tdc_abi_version", "tdc_create", "tdc_destroy", "tdc_last_error", "tdc_load_weights", "tdc_workspace_bytes",
     "tdc_qformer_forward", "tdc_proj_norm", "tdc_compress", "tdc_compress_multicast", "tdc_frames_workspace_bytes",
-    "tdc_compress_frames", "tdc_linear", "tdc_gelu_mlp", "tdc_avg_pool_tokens",
+    "tdc_compress_frames", "tdc_linear", "tdc_linear_layernorm", "tdc_gelu_mlp", "tdc_avg_pool_tokens",
     "tdc_convert", "tdc_layernorm", "tdc_attention", "tdc_residual_add", "tdc_segment_workspace_bytes", "tdc_segment_boundaries", "tdc_set_profiling", "tdc_get_profile", "tdc_reset_profile", "tdc_launch_count",
 ]
 
@@ -80,6 +80,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.tdc_compress_frames.restype = C.c_int
     lib.tdc_proj_norm.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp, sz, vp]
     lib.tdc_linear.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.tdc_linear_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, C.c_float, vp, vp, i32, i32, i32, vp]
+    lib.tdc_linear_layernorm.restype = C.c_int
     lib.tdc_gelu_mlp.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.tdc_avg_pool_tokens.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
     lib.tdc_convert.argtypes = [vp, i32, vp, i32, i64, vp]

@@ -20,7 +20,7 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libtdc_b200.so"
 OBJ_DIR = REPO_ROOT / "build" / "obj"
 
-SOURCES = ["gemm_sm100.cu", "attention.cu", "rowops.cu", "segment.cu", "frontend.cu", "tdc_api.cu"]
+SOURCES = ["gemm_sm100.cu", "gemm_ln_sm100.cu", "attention.cu", "rowops.cu", "segment.cu", "frontend.cu", "tdc_api.cu"]
 HEADERS = ["tdc_ptx.cuh", "tdc_gemm.cuh", "tdc_kernels.cuh"]
 
 NVCC_FLAGS = [

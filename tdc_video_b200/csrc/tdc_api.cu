@@ -21,6 +21,7 @@
 #include "tdc_gemm.cuh"
 #include "tdc_kernels.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <cstdio>
 #include <string>
@@ -363,6 +364,14 @@ int gemm(tdc_handle* h, int cls, cudaStream_t s, const void* a, long long lda, c
   return gemm_launch(p, s, err);
 }
 
+// dense + residual + LayerNorm of a post-LN sub-layer (Qformer.py:285-289, 371-375) on slab rows [first, first + count):
+// ONE kernel (gemm_ln_sm100.cu) when the width fits a cluster (N <= 768), otherwise GEMM -> fp32 `pre` -> LayerNorm.
+// TDC_NO_FUSED_LN=1 (dev knob, read once) forces the two-kernel form for A/B measurements.
+bool fused_ln_enabled(int n) {
+  static const bool off = [] { const char* e = getenv("TDC_NO_FUSED_LN"); return e != nullptr && atoi(e) == 1; }();
+  return !off && gemm_ln_supported(n);
+}
+
 // Where the cross-attention K/V of a row batch live: one dense [slab_rows, 2H] (K | V) matrix per cross layer
 // (`slab_stride` elements apart, row pitch `pitch`).  Row r's KV tokens: seg1 tokens at slab row r*seg1 + t, then
 // seg2 tokens at base2 + r*seg2 + t, then seg3 tokens at base3 + t shared by ALL rows (the image_newline tokens).
@@ -405,7 +414,21 @@ int qformer_layers(tdc_handle* h, const ForwardCall& f, long long row0, long lon
   }
 
   const long long MQ = rows * K, MT = rows * T, MA = rows * n;
-  auto ln = [&](const float* g, const float* b, long long first, long long count) -> int {
+  const bool fused = fused_ln_enabled(H);
+  // h[first .. first + count) = LN(a . wt^T + bias + h) * g + b   (a: bf16 [count, kdim])
+  auto dense_ln = [&](const __nv_bfloat16* a, int kdim, const __nv_bfloat16* wt, const float* bias, const float* g,
+                      const float* b, long long first, long long count) -> int {
+    if (fused) {
+      GemmLnProblem p;
+      p.a = a; p.lda = kdim; p.w = wt; p.ldw = kdim; p.m = static_cast<int>(count); p.n = H; p.k = kdim;
+      p.bias = bias; p.resid = w.h_f32 + first * H; p.ldr = H; p.gamma = g; p.beta = b; p.eps = c.ln_eps;
+      p.out_f32 = w.h_f32 + first * H; p.out_bf16 = w.h_bf16 + first * H; p.ldo = H;
+      KernelScope ks(h, TDC_K_QUERY_GEMM, s);
+      return gemm_ln_launch(p, s, &err);
+    }
+    const int rc = gemm(h, TDC_K_QUERY_GEMM, s, a, kdim, wt, kdim, bias, w.pre + first * H, H, count, H, kdim,
+                        EPI_BIAS_F32, &err);
+    if (rc != TDC_OK) return rc;
     KernelScope ks(h, TDC_K_ROWOPS, s);
     // h = LN(pre + h): the residual add of the post-LN block lives here, not in the GEMM epilogue
     return layernorm_launch(w.pre + first * H, H, w.h_f32 + first * H, H, g, b, c.ln_eps, w.h_f32 + first * H,
@@ -436,8 +459,7 @@ int qformer_layers(tdc_handle* h, const ForwardCall& f, long long row0, long lon
       KernelScope ks(h, TDC_K_ATTENTION, s);
       TDC_TRY(attention_launch(a, s, &err));
     }
-    TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.ctx, H, lw.w_ao, H, lw.b_ao, w.pre, H, M_self, H, H, EPI_BIAS_F32, &err));
-    TDC_TRY(ln(lw.ln_a_g, lw.ln_a_b, 0, M_self));
+    TDC_TRY(dense_ln(w.ctx, H, lw.w_ao, lw.b_ao, lw.ln_a_g, lw.ln_a_b, 0, M_self));
     }
     if (f.l0_out != nullptr) {   // pre-pass: the state after layer 0's self-attention block, one "row" per set
       KernelScope ks(h, TDC_K_ROWOPS, s);
@@ -465,21 +487,17 @@ int qformer_layers(tdc_handle* h, const ForwardCall& f, long long row0, long lon
         KernelScope ks(h, TDC_K_ATTENTION, s);
         TDC_TRY(attention_launch(a, s, &err));
       }
-      TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.ctx, H, lw.w_co, H, lw.b_co, w.pre, H, MQ, H, H, EPI_BIAS_F32, &err));
-      TDC_TRY(ln(lw.ln_c_g, lw.ln_c_b, 0, MQ));
+      TDC_TRY(dense_ln(w.ctx, H, lw.w_co, lw.b_co, lw.ln_c_g, lw.ln_c_b, 0, MQ));
     }
 
     // ---- feed-forward: query tokens and text tokens use different weights
     TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16, H, lw.w_fq1, H, lw.b_fq1, w.mid, I, MQ, I, H, EPI_BIAS_GELU_BF16,
                  &err));
-    TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.mid, I, lw.w_fq2, I, lw.b_fq2, w.pre, H, MQ, H, I, EPI_BIAS_F32, &err));
-    TDC_TRY(ln(lw.ln_fq_g, lw.ln_fq_b, 0, MQ));
+    TDC_TRY(dense_ln(w.mid, I, lw.w_fq2, lw.b_fq2, lw.ln_fq_g, lw.ln_fq_b, 0, MQ));
     if (text_live) {
       TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16 + MQ * H, H, lw.w_ft1, H, lw.b_ft1, w.mid, I, MT, I, H,
                    EPI_BIAS_GELU_BF16, &err));
-      TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.mid, I, lw.w_ft2, I, lw.b_ft2, w.pre + MQ * H, H, MT, H, I,
-                   EPI_BIAS_F32, &err));
-      TDC_TRY(ln(lw.ln_ft_g, lw.ln_ft_b, MQ, MT));
+      TDC_TRY(dense_ln(w.mid, I, lw.w_ft2, lw.b_ft2, lw.ln_ft_g, lw.ln_ft_b, MQ, MT));
     }
   }
 
@@ -1057,6 +1075,19 @@ int tdc_linear(const void* x, const void* w, const float* bias, void* y, int32_t
   const char* err = nullptr;
   const int rc = gemm_launch(p, static_cast<cudaStream_t>(stream), &err);
   if (rc != TDC_OK) g_create_error = err ? err : "tdc_linear failed";
+  return rc;
+}
+
+int tdc_linear_layernorm(const void* x, const void* w, const float* bias, const float* resid, const float* gamma,
+                         const float* beta, float eps, float* y_f32, void* y_bf16, int32_t m, int32_t n, int32_t k,
+                         tdc_stream_t stream) {
+  if (m == 0) return TDC_OK;
+  GemmLnProblem p;
+  p.a = x; p.lda = k; p.w = w; p.ldw = k; p.m = m; p.n = n; p.k = k; p.bias = bias; p.resid = resid; p.ldr = n;
+  p.gamma = gamma; p.beta = beta; p.eps = eps > 0.f ? eps : 1e-12f; p.out_f32 = y_f32; p.out_bf16 = y_bf16; p.ldo = n;
+  const char* err = nullptr;
+  const int rc = gemm_ln_launch(p, static_cast<cudaStream_t>(stream), &err);
+  if (rc != TDC_OK) g_create_error = err ? err : "tdc_linear_layernorm failed";
   return rc;
 }
 

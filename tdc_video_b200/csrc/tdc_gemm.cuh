@@ -37,6 +37,27 @@ struct GemmProblem {
 // non-null) points at a static description.
 int gemm_launch(const GemmProblem& p, cudaStream_t stream, const char** err);
 
+// GEMM + residual + LayerNorm in one kernel (gemm_ln_sm100.cu):
+//   out_f32 = LayerNorm(A . W^T + bias + resid) * gamma + beta,  out_bf16 = bf16(out_f32)
+// — BertSelfOutput / BertOutput of the reference (tdc/Qformer.py:285-289, 371-375).  resid may alias out_f32.
+struct GemmLnProblem {
+  const void* a = nullptr;  // bf16 [M, K]
+  const void* w = nullptr;  // bf16 [N, K]
+  long long lda = 0, ldw = 0;
+  int m = 0, n = 0, k = 0;
+  const float* bias = nullptr;   // [N]
+  const float* resid = nullptr;  // fp32 [M, N], pitch ldr
+  long long ldr = 0;
+  const float* gamma = nullptr;  // [N]
+  const float* beta = nullptr;   // [N]
+  float eps = 1e-12f;
+  float* out_f32 = nullptr;      // fp32 [M, N], pitch ldo
+  void* out_bf16 = nullptr;      // bf16 [M, N], pitch ldo
+  long long ldo = 0;
+};
+bool gemm_ln_supported(int n);   // N <= 768 (a cluster of up to 3 CTAs x 256 columns holds one LayerNorm row)
+int gemm_ln_launch(const GemmLnProblem& p, cudaStream_t stream, const char** err);
+
 // Number of kernels gemm_launch enqueues (always 1) — kept for launch accounting.
 inline int gemm_launch_count() { return 1; }
 
