@@ -243,6 +243,12 @@ int tdc_attention(const void* q, const void* k, const void* v, void* out, int64_
                   int64_t q_base2, int32_t kv_seg1, int32_t kv_seg2, int64_t kv_base1, int64_t kv_base2,
                   const int32_t* kv_len, const uint32_t* kv_mask, tdc_stream_t stream);
 
+/* replaces: F.interpolate(x.permute(0,2,1).view(bs,-1,s,s).float(), size=(S,S), mode="bilinear", align_corners=False)
+ * and the permute back — the query groups whose grid differs from the final token grid, cambrian_arch.py:1107-1131.
+ * Token-major in and out: in [bs, side_in^2, d] -> out [bs, side_out^2, d]; fp32 arithmetic. */
+int tdc_resize_tokens_bilinear(const void* in, int32_t in_dtype, int32_t bs, int32_t side_in, int32_t side_out,
+                               int32_t d, void* out, int32_t out_dtype, tdc_stream_t stream);
+
 /* out = a + b in fp32 (out_f32 and/or out_bf16 may be NULL) — the outer residual of an SVA layer (:399). */
 int tdc_residual_add(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t count,
                      tdc_stream_t stream);

@@ -118,8 +118,26 @@ def token_sampler(sd, prefix, queries, context, latents, masks, num_layers: int,
     return queries
 
 
+def sva_frames_groups(sd, tower_feats: Sequence[torch.Tensor], image_sizes: Sequence[Tuple[int, int]],
+                      query_sides: Sequence[int], final_side: int, num_layers: int, num_heads: int = 16) -> torch.Tensor:
+    """cambrian_arch.py:1017-1148 for several query groups (`query_num_list`): group g uses `vision_query[g]` and
+    `vision_sampler_{g}`; a group whose grid differs from the final one is resized with
+    F.interpolate(..., mode="bilinear", align_corners=False) in fp32 (:1107-1131, input_high_res); the groups are
+    concatenated on the feature axis (:1148).  -> [bs, final_side^2, groups * hidden]"""
+    outs = []
+    for g, q in enumerate(query_sides):
+        o = sva_frames(sd, tower_feats, image_sizes, q, num_layers, num_heads, group=g)
+        bs = o.shape[0]
+        if q != final_side:
+            x = o.permute(0, 2, 1).contiguous().view(bs, -1, q, q)
+            x = F.interpolate(x.float(), size=(final_side, final_side), mode="bilinear", align_corners=False)
+            o = x.permute(0, 2, 3, 1).contiguous().flatten(1, 2)
+        outs.append(o)
+    return torch.cat(outs, -1)
+
+
 def sva_frames(sd, tower_feats: Sequence[torch.Tensor], image_sizes: Sequence[Tuple[int, int]], query_side: int,
-               num_layers: int, num_heads: int = 16) -> torch.Tensor:
+               num_layers: int, num_heads: int = 16, group: int = 0) -> torch.Tensor:
     """cambrian_arch.py:1002-1053 for one query group (group 0) at final resolution: tower features
     [bs, grid_t^2, C_t] -> query features [bs, query_side^2, hidden]."""
     feats = [mm_projector_aux(sd, f"mm_projector_aux_{t}", f) for t, f in enumerate(tower_feats)]
@@ -127,9 +145,9 @@ def sva_frames(sd, tower_feats: Sequence[torch.Tensor], image_sizes: Sequence[Tu
     hidden = feats[0].shape[-1]
     nq = query_side * query_side
     context = feats[0].mean(1).view(bs, 1, 1, -1).expand(-1, nq, 1, -1).flatten(0, 1)            # :1009-1011, 1024-1026
-    queries = _t(sd["vision_query"])[0].view(1, 1, 1, -1).expand(bs, nq, -1, -1).flatten(0, 1)    # :1018-1023
+    queries = _t(sd["vision_query"])[group].view(1, 1, 1, -1).expand(bs, nq, -1, -1).flatten(0, 1)  # :1018-1023
     latents = [rearrange_windows(f, query_side) for f in feats]
     masks = [torch.cat([window_masks(image_sizes[b], int(f.shape[1] ** 0.5), query_side) for b in range(bs)], 0)
              for f in feats]
-    out = token_sampler(sd, "vision_sampler_0.", queries, context, latents, masks, num_layers, num_heads)
+    out = token_sampler(sd, f"vision_sampler_{group}.", queries, context, latents, masks, num_layers, num_heads)
     return out.view(bs, nq, hidden)

@@ -8,6 +8,8 @@
 #include "tdc_kernels.cuh"
 #include "tdc_ptx.cuh"
 
+#include <cuda_fp16.h>
+
 namespace tdc {
 
 namespace {
@@ -155,6 +157,63 @@ __global__ void __launch_bounds__(256) broadcast_rows_kernel(const float* __rest
   }
 }
 
+// F.interpolate(mode="bilinear", align_corners=False) on a token grid kept token-major: in [bs, s_in^2, d] ->
+// out [bs, s_out^2, d] (the reference permutes to [bs, d, s, s], interpolates in fp32 and permutes back,
+// cambrian_arch.py:1107-1131).  Source coordinate of output cell o: max((o + 0.5) * s_in / s_out - 0.5, 0).
+__global__ void __launch_bounds__(256) resize_tokens_bilinear_kernel(const void* __restrict__ in, int in_dtype, int s_in,
+                                                                     int s_out, int d, void* __restrict__ out,
+                                                                     int out_dtype, long long tokens_out) {
+  const long long tok = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (tok >= tokens_out) return;
+  const int lane = threadIdx.x & 31;
+  const long long b = tok / (s_out * s_out);
+  const int oy = static_cast<int>(tok % (s_out * s_out)) / s_out, ox = static_cast<int>(tok % s_out);
+  const float scale = static_cast<float>(s_in) / static_cast<float>(s_out);
+  const float fy = fmaxf((oy + 0.5f) * scale - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * scale - 0.5f, 0.f);
+  const int y0 = min(static_cast<int>(fy), s_in - 1), x0 = min(static_cast<int>(fx), s_in - 1);
+  const int y1 = min(y0 + 1, s_in - 1), x1 = min(x0 + 1, s_in - 1);
+  const float ly = fy - y0, lx = fx - x0;
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const size_t isz = in_dtype == TDC_F32 ? 4 : 2, osz = out_dtype == TDC_F32 ? 4 : 2;
+  const uint8_t* base = static_cast<const uint8_t*>(in) + static_cast<size_t>(b) * s_in * s_in * d * isz;
+  auto load4 = [&](int y, int x, int j) -> float4 {
+    const uint8_t* p = base + (static_cast<size_t>(y) * s_in + x) * d * isz;
+    if (in_dtype == TDC_F32) return __ldg(reinterpret_cast<const float4*>(p) + j);
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p) + j);
+    if (in_dtype == TDC_BF16) {
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+      const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+      return make_float4(__low2float(a), __high2float(a), __low2float(c), __high2float(c));
+    }
+    const __half2 a = *reinterpret_cast<const __half2*>(&raw.x);
+    const __half2 c = *reinterpret_cast<const __half2*>(&raw.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(c), __high2float(c));
+  };
+  uint8_t* dst = static_cast<uint8_t*>(out) + static_cast<size_t>(tok) * d * osz;
+  for (int j = lane; j < d / 4; j += 32) {
+    const float4 a = load4(y0, x0, j), bq = load4(y0, x1, j), c = load4(y1, x0, j), e = load4(y1, x1, j);
+    float4 v;
+    v.x = w00 * a.x + w01 * bq.x + w10 * c.x + w11 * e.x;
+    v.y = w00 * a.y + w01 * bq.y + w10 * c.y + w11 * e.y;
+    v.z = w00 * a.z + w01 * bq.z + w10 * c.z + w11 * e.z;
+    v.w = w00 * a.w + w01 * bq.w + w10 * c.w + w11 * e.w;
+    if (out_dtype == TDC_F32) {
+      reinterpret_cast<float4*>(dst)[j] = v;
+    } else if (out_dtype == TDC_BF16) {
+      uint2 pk;
+      pk.x = pack_bf16x2(v.x, v.y);
+      pk.y = pack_bf16x2(v.z, v.w);
+      reinterpret_cast<uint2*>(dst)[j] = pk;
+    } else {
+      const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+      reinterpret_cast<uint2*>(dst)[j] = pk;
+    }
+  }
+}
+
 int launched(const char** err) {
   const cudaError_t rc = cudaGetLastError();
   if (rc != cudaSuccess) {
@@ -219,6 +278,19 @@ int assemble_static_launch(const __nv_bfloat16* xv, const __nv_bfloat16* xa, con
   }
   assemble_static_kernel<<<static_cast<unsigned>((toks + 7) / 8), 256, 0, stream>>>(xv, xa, newline, chunks, side, ta, d,
                                                                                     out, out_dtype);
+  return launched(err);
+}
+
+int resize_tokens_bilinear_launch(const void* in, int in_dtype, int bs, int s_in, int s_out, int d, void* out,
+                                  int out_dtype, cudaStream_t stream, const char** err) {
+  const long long toks = static_cast<long long>(bs) * s_out * s_out;
+  if (toks <= 0) return TDC_OK;
+  if (d % 4 != 0 || s_in <= 0 || s_out <= 0) {
+    if (err) *err = "resize_tokens_bilinear: d must be a multiple of 4, sides positive";
+    return TDC_EINVAL;
+  }
+  resize_tokens_bilinear_kernel<<<static_cast<unsigned>((toks + 7) / 8), 256, 0, stream>>>(in, in_dtype, s_in, s_out, d,
+                                                                                          out, out_dtype, toks);
   return launched(err);
 }
 

@@ -1147,6 +1147,21 @@ int tdc_attention(const void* q, const void* k, const void* v, void* out, int64_
   return rc;
 }
 
+int tdc_resize_tokens_bilinear(const void* in, int32_t in_dtype, int32_t bs, int32_t side_in, int32_t side_out,
+                               int32_t d, void* out, int32_t out_dtype, tdc_stream_t stream) {
+  if (bs == 0) return TDC_OK;
+  if (in == nullptr || out == nullptr || bs < 0 || in_dtype < TDC_BF16 || in_dtype > TDC_F32 || out_dtype < TDC_BF16 ||
+      out_dtype > TDC_F32) {
+    g_create_error = "tdc_resize_tokens_bilinear: null pointer / bad argument";
+    return TDC_EINVAL;
+  }
+  const char* err = nullptr;
+  const int rc = resize_tokens_bilinear_launch(in, in_dtype, bs, side_in, side_out, d, out, out_dtype,
+                                               static_cast<cudaStream_t>(stream), &err);
+  if (rc != TDC_OK) g_create_error = err ? err : "tdc_resize_tokens_bilinear failed";
+  return rc;
+}
+
 int tdc_residual_add(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t count,
                      tdc_stream_t stream) {
   if (count == 0) return TDC_OK;

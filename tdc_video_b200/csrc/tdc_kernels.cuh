@@ -108,6 +108,9 @@ int pool_static_queries_launch(const __nv_bfloat16* xv, const float* newline, in
 // static_out[c] = [(side visual tokens, newline) x side | ta audio tokens] (the key frame as it passes through)
 int assemble_static_launch(const __nv_bfloat16* xv, const __nv_bfloat16* xa, const float* newline, int chunks, int side,
                            int ta, int d, void* out, int out_dtype, cudaStream_t stream, const char** err);
+// bilinear (align_corners = False) resize of a token grid, token-major: [bs, s_in^2, d] -> [bs, s_out^2, d]
+int resize_tokens_bilinear_launch(const void* in, int in_dtype, int bs, int s_in, int s_out, int d, void* out,
+                                  int out_dtype, cudaStream_t stream, const char** err);
 // rows [row0, row0 + count) of each of `slabs` matrices [*, width] (slab_stride elements apart) = src[slab] as bf16
 int broadcast_rows_launch(const float* src, int width, int slabs, __nv_bfloat16* dst, long long slab_stride,
                           long long row0, int count, cudaStream_t stream, const char** err);

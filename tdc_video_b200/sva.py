@@ -106,11 +106,19 @@ def _cross_attention_layer(hidden: int, window_sides: Sequence[int]) -> nn.Modul
 
 
 class SVAConnector(nn.Module):
-    """`mm_projector_aux_{t}` + `vision_query` + `vision_sampler_0` of the reference model (one query group whose
-    grid equals the final token grid: query_num_list == [image_token_len], the shipped configuration)."""
+    """`mm_projector_aux_{t}` + `vision_query` + `vision_sampler_{g}` of the reference model.
+
+    Default: one query group whose grid equals the final token grid (query_num_list == [image_token_len], the
+    shipped configuration).  `query_sides` = the grid side of every query group (sqrt of `query_num_list`,
+    cambrian_arch.py:1017-1053): group g gets its own `vision_query[g]` and `vision_sampler_{g}` over windows of
+    side grid_t / query_sides[g]; groups whose grid differs from the final `query_side` are bilinearly resized to it
+    (:1107-1131) and all groups are concatenated on the feature axis (:1148), as the reference does.
+    Not provided: `VisionAggregationLayer` (layer_type "sep") — the reference never constructs it (VisionTokenSampler
+    is only ever built with the default "joint", cambrian_arch.py:101, 128, 286) — and the samplers inside the LLM
+    layers (`vision_sampler_layers`, not connector_only), which belong to the language model."""
 
     def __init__(self, tower_dims: Sequence[int], window_sides: Sequence[int], hidden: int = 1024, query_side: int = 12,
-                 num_layers: int = 3):
+                 num_layers: int = 3, query_sides: Optional[Sequence[int]] = None):
         super().__init__()
         if len(tower_dims) != 2 or len(window_sides) != 2:
             raise NotImplementedError("two vision towers (SigLIP + DINOv2) as in the reference; the attention kernel "
@@ -118,17 +126,26 @@ class SVAConnector(nn.Module):
         if hidden % 64 != 0:
             raise ValueError("libtdc_b200 attention has head size 64: hidden must be a multiple of 64 "
                              "(reference: 1024 = 16 heads x 64)")
-        if sum(s * s for s in window_sides) > 32:
-            raise ValueError("at most 32 KV tokens per query (per-row key mask is 32 bits)")
         self.hidden, self.query_side, self.num_layers = hidden, query_side, num_layers
         self.window_sides = tuple(int(s) for s in window_sides)
+        self.tower_grids = tuple(query_side * s for s in self.window_sides)
+        self.query_sides = tuple(int(q) for q in (query_sides if query_sides is not None else (query_side,)))
+        self.group_window_sides = []
+        for q in self.query_sides:
+            if any(g % q for g in self.tower_grids):
+                raise ValueError(f"query grid side {q} does not divide the tower grids {self.tower_grids}")
+            sides = tuple(g // q for g in self.tower_grids)
+            if sum(s * s for s in sides) > 32:
+                raise ValueError("at most 32 KV tokens per query (per-row key mask is 32 bits)")
+            self.group_window_sides.append(sides)
         for t, c in enumerate(tower_dims):
             setattr(self, f"mm_projector_aux_{t}", nn.Sequential(nn.Linear(c, hidden), nn.GELU(),
                                                                  nn.Linear(hidden, hidden), nn.LayerNorm(hidden)))
-        self.vision_query = nn.Parameter(torch.randn(1, hidden))
-        self.vision_sampler_0 = _Params()
-        self.vision_sampler_0.layers = nn.ModuleList(
-            [_cross_attention_layer(hidden, self.window_sides) for _ in range(num_layers)])
+        self.vision_query = nn.Parameter(torch.randn(len(self.query_sides), hidden))
+        for g, sides in enumerate(self.group_window_sides):
+            sampler = _Params()
+            sampler.layers = nn.ModuleList([_cross_attention_layer(hidden, sides) for _ in range(num_layers)])
+            setattr(self, f"vision_sampler_{g}", sampler)
         self._bf16 = {}
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._bf16.clear())
         self.eval()
@@ -145,14 +162,14 @@ class SVAConnector(nn.Module):
             self._bf16[key] = lin.weight.detach().to(torch.bfloat16).contiguous()
         return self._bf16[key]
 
-    def _kv_folded(self, li: int, t: int):
+    def _kv_folded(self, li: int, t: int, g: int = 0):
         """K and V projections of one tower as ONE GEMM over the shared normalised input: both are
         Linear(LayerNorm(x)) of the same x (vision_sampler.py:192-217), and LayerNorm(x) = xhat * gamma + beta with
         xhat = (x - mean) / std common to the two, so W (gamma * xhat + beta) = (W diag(gamma)) xhat + W beta.
         Returns ([2H, H] bf16 weight, [2H] fp32 bias, ones/zeros LayerNorm parameters); made once."""
-        key = ("kv", li, t)
+        key = ("kv", g, li, t)
         if key not in self._bf16:
-            ca = self.vision_sampler_0.layers[li].cross_attn
+            ca = getattr(self, f"vision_sampler_{g}").layers[li].cross_attn
             ws, bs = [], []
             for name in (f"k_proj_{t}", f"v_proj_{t}"):
                 ln, lin = getattr(ca, name)
@@ -167,24 +184,42 @@ class SVAConnector(nn.Module):
     @torch.no_grad()
     def forward(self, tower_feats: Sequence[torch.Tensor], image_sizes: Sequence[Tuple[int, int]]) -> torch.Tensor:
         """tower_feats[t]: [bs, grid_t^2, C_t] (CUDA); image_sizes[b] = (width, height) of frame b before padding.
-        Returns the query features [bs, Q^2, hidden] (bf16) that feed `mm_projector` (cambrian_arch.py:1146-1150)."""
+        Returns the query features [bs, Q^2, groups * hidden] (bf16) that feed `mm_projector`
+        (cambrian_arch.py:1146-1150)."""
         if self.training:
             raise RuntimeError("SVAConnector is inference-only (eval mode)")
         if not tower_feats[0].is_cuda:
             raise RuntimeError("SVAConnector needs CUDA tensors: there is no CPU fallback")
+        outs = []
+        for g, q in enumerate(self.query_sides):
+            o = self._forward_group(g, tower_feats, image_sizes)                   # [bs, q^2, H] bf16
+            if q != self.query_side:                                               # :1107-1131 (input_high_res)
+                lib = _lib.load_library()
+                r = torch.empty((o.shape[0], self.query_side ** 2, self.hidden), dtype=torch.bfloat16, device=o.device)
+                with torch.cuda.device(o.device):
+                    rc = lib.tdc_resize_tokens_bilinear(_ptr(o), _lib.TDC_BF16, o.shape[0], q, self.query_side,
+                                                        self.hidden, _ptr(r), _lib.TDC_BF16, _stream(o.device))
+                _lib.check(rc, None, "tdc_resize_tokens_bilinear")
+                o = r
+            outs.append(o)
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=-1)               # :1148
+
+    def _forward_group(self, group: int, tower_feats, image_sizes) -> torch.Tensor:
         lib = _lib.load_library()
         dev = tower_feats[0].device
-        bs, Q, H = tower_feats[0].shape[0], self.query_side, self.hidden
+        bs, Q, H = tower_feats[0].shape[0], self.query_sides[group], self.hidden
+        window_sides = self.group_window_sides[group]
+        sampler = getattr(self, f"vision_sampler_{group}")
         R = bs * Q * Q
         grids = [int(round(f.shape[1] ** 0.5)) for f in tower_feats]
-        for g, s in zip(grids, self.window_sides):
+        for g, s in zip(grids, window_sides):
             if g != Q * s:
                 raise ValueError(f"tower grid {g} != query_side {Q} x window side {s}")
         # --- mm_projector_aux_t: Linear . GELU . Linear . LayerNorm  (cambrian_arch.py:1002-1013)
         latents, feat0 = [], None
         for t, x in enumerate(tower_feats):
             seq = getattr(self, f"mm_projector_aux_{t}")
-            r = self.window_sides[t]
+            r = window_sides[t]
             # tokens under every query, window-major (cambrian_arch.py:624-645).  The projector acts on each token
             # separately and the context is a mean over tokens, so the rearrangement is applied to the (narrow,
             # bf16) tower features instead of the projector's fp32 output: pure data movement, fused with the cast.
@@ -197,15 +232,15 @@ class SVAConnector(nn.Module):
                 feat0 = f32.view(bs, grids[t] * grids[t], H)
             latents.append(f32)
         context = avg_pool_tokens(feat0, 1).reshape(bs, H)                       # global context = token mean (:1009)
-        q32 = self.vision_query.detach()[0].float().view(1, H).expand(R, H).contiguous()
+        q32 = self.vision_query.detach()[group].float().view(1, H).expand(R, H).contiguous()
         q16 = q32.to(torch.bfloat16)
         mask = torch.from_numpy(window_mask_bits(image_sizes, grids, Q).view(np.int32)).to(dev)
-        n0, n1 = self.window_sides[0] ** 2, self.window_sides[1] ** 2
+        n0, n1 = window_sides[0] ** 2, window_sides[1] ** 2
         rows0 = R * n0                                                           # K/V rows of tower 0 precede tower 1's
         kv = torch.empty((R * (n0 + n1), 2 * H), dtype=torch.bfloat16, device=dev)   # row = [K | V] of one token
         xhat = torch.empty((R * max(n0, n1), H), dtype=torch.bfloat16, device=dev)
         att = torch.empty((R, H), dtype=torch.bfloat16, device=dev)
-        for li, layer in enumerate(self.vision_sampler_0.layers):
+        for li, layer in enumerate(sampler.layers):
             ca = layer.cross_attn
             # proj_context + cat + proj_in (vision_sampler.py:346-360); the context is one vector per frame
             ctx = linear(context, self._w(layer.proj_context))                   # [bs, H] bf16
@@ -214,7 +249,7 @@ class SVAConnector(nn.Module):
             qs = linear(_layernorm(q1, ca.q_proj[0]), self._w(ca.q_proj[1]))
             for t, (lat, n, off) in enumerate(zip(latents, (n0, n1), (0, rows0))):
                 pos = getattr(layer, f"pos_embed_{t}", None)
-                w_kv, b_kv, ones, zeros = self._kv_folded(li, t)
+                w_kv, b_kv, ones, zeros = self._kv_folded(li, t, group)
                 # one normalisation pass (statistics only) shared by K and V, then one N = 2H GEMM
                 with torch.cuda.device(dev):
                     rc = lib.tdc_layernorm(_ptr(lat), None if pos is None else _ptr(pos.detach().float().contiguous()),

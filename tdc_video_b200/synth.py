@@ -167,8 +167,31 @@ def make_sva_state_dict(hidden: int, tower_dims, window_sides, num_layers: int, 
         lin(f"mm_projector_aux_{t}.2", hidden, hidden, bias=True)
         ln(f"mm_projector_aux_{t}.3", hidden)
     sd["vision_query"] = rs.standard_normal((1, hidden)).astype(f32)
+    _sva_sampler_weights(sd, rs, "vision_sampler_0.", hidden, window_sides, num_layers, stress)
+    return sd
+
+
+def add_sva_group(sd: Dict[str, np.ndarray], group: int, hidden: int, window_sides, num_layers: int, seed: int,
+                  stress: float = 1.0) -> None:
+    """One more query group (`vision_query[group]`, `vision_sampler_{group}`; cambrian_arch.py:92-110, 139-142)."""
+    rs = np.random.RandomState(seed)
+    assert sd["vision_query"].shape[0] == group
+    sd["vision_query"] = np.concatenate([sd["vision_query"], rs.standard_normal((1, hidden)).astype(np.float32)], 0)
+    _sva_sampler_weights(sd, rs, f"vision_sampler_{group}.", hidden, window_sides, num_layers, stress)
+
+
+def _sva_sampler_weights(sd, rs, prefix, hidden, window_sides, num_layers, stress):
+    f32 = np.float32
+
+    def lin(name, out_f, in_f, bias=False, scale=None):
+        sd[name + ".weight"] = (rs.standard_normal((out_f, in_f)) * (scale or 1.0 / np.sqrt(in_f))).astype(f32)
+
+    def ln(name, n):
+        sd[name + ".weight"] = (1.0 + 0.1 * rs.standard_normal((n,))).astype(f32)
+        sd[name + ".bias"] = (0.1 * rs.standard_normal((n,))).astype(f32)
+
     for i in range(num_layers):
-        p = f"vision_sampler_0.layers.{i}."
+        p = f"{prefix}layers.{i}."
         lin(p + "proj_context", hidden, hidden)
         lin(p + "proj_in", hidden, 2 * hidden)
         lin(p + "proj_out.linear_1", hidden, hidden)

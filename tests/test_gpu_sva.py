@@ -89,3 +89,38 @@ def test_attention_kv_mask_building_block():
     ref = ref.transpose(1, 2).reshape(R, heads * 64)
     assert torch.isfinite(out.float()).all()
     _check(out, ref, "masked attention")
+
+
+def test_sva_two_query_groups_vs_oracle():
+    """Two query groups (query_num_list = [16, 4] on 8 x 8 tower grids): per-group samplers, bilinear resize of the
+    coarse group on the GPU (tdc_resize_tokens_bilinear), feature concat — cambrian_arch.py:1017-1148."""
+    from oracle.synth import add_sva_group
+    from tdc_video_b200.sva import SVAConnector
+    hidden, dims, layers, sizes = 128, (96, 64), 2, [(640, 360), (384, 384), (300, 500)]
+    sd = make_sva_state_dict(hidden, dims, (2, 2), layers, seed=5, stress=1.5)
+    add_sva_group(sd, 1, hidden, (4, 4), layers, seed=6, stress=1.5)
+    rs = np.random.RandomState(2)
+    tower = [torch.from_numpy(rs.standard_normal((len(sizes), 64, c)).astype(np.float32)) for c in dims]
+    mod = SVAConnector(dims, (2, 2), hidden=hidden, query_side=4, num_layers=layers, query_sides=(4, 2))
+    mod.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    mod = mod.cuda().eval()
+    out = mod([t.cuda() for t in tower], sizes)
+    torch.cuda.synchronize()
+    ref = sva_oracle.sva_frames_groups(sd, tower, sizes, (4, 2), 4, layers, num_heads=hidden // 64)
+    assert out.shape == ref.shape == (3, 16, 2 * hidden)
+    _check(out, ref, "sva two query groups")
+
+
+@pytest.mark.parametrize("s_in,s_out", [(2, 4), (6, 12), (12, 8), (5, 5)])
+def test_resize_tokens_bilinear_matches_torch(s_in, s_out):
+    import torch.nn.functional as F
+    from tdc_video_b200 import _lib
+    from tdc_video_b200.engine import _ptr, _stream
+    lib = _lib.load_library()
+    x = torch.randn(3, s_in * s_in, 64, device="cuda")
+    out = torch.empty(3, s_out * s_out, 64, device="cuda")
+    assert lib.tdc_resize_tokens_bilinear(_ptr(x), _lib.TDC_F32, 3, s_in, s_out, 64, _ptr(out), _lib.TDC_F32,
+                                          _stream(x.device)) == 0
+    ref = F.interpolate(x.permute(0, 2, 1).reshape(3, 64, s_in, s_in), size=(s_out, s_out), mode="bilinear",
+                        align_corners=False).permute(0, 2, 3, 1).flatten(1, 2)
+    assert torch.allclose(out, ref, atol=1e-5)

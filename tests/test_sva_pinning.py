@@ -77,3 +77,47 @@ def test_token_sampler_and_projector_equal_reference(hidden, sides, layers, size
     got = sva_oracle.sva_frames(sd, tower, sizes, Q, layers)
     assert got.shape == ref.shape
     assert float((got - ref).abs().max()) <= 5e-5
+
+
+def test_two_query_groups_equal_reference_modules():
+    """query_num_list with two groups (cambrian_arch.py:1017-1148): group 1's coarser grid goes through its own
+    VisionTokenSampler over larger windows, is resized with F.interpolate(bilinear, align_corners=False) to the final
+    grid and concatenated on the feature axis.  Reference modules + the literal interpolate lines vs the oracle."""
+    import torch.nn.functional as F
+    from oracle.synth import add_sva_group
+    vs = _load_vision_sampler()
+    hidden, dims, layers, sizes = 128, (96, 64), 2, [(640, 360), (384, 384)]
+    final, coarse = 4, 2                               # tower grids 8 x 8: windows 2 x 2 (final) and 4 x 4 (coarse)
+    sd = make_sva_state_dict(hidden, dims, (2, 2), layers, seed=5, stress=2.0)
+    add_sva_group(sd, 1, hidden, (4, 4), layers, seed=6, stress=2.0)
+    bs = len(sizes)
+    rs = np.random.RandomState(2)
+    tower = [torch.from_numpy(rs.standard_normal((bs, 64, c)).astype(np.float32)) for c in dims]
+    from oracle import harness
+    arch = harness._load_cambrian_arch()
+
+    class Bare(arch.CambrianMetaForCausalLM):
+        def get_model(self):
+            return None
+
+    with torch.no_grad():
+        feats = [sva_oracle.mm_projector_aux(sd, f"mm_projector_aux_{t}", tower[t]) for t in range(2)]
+        outs = []
+        for g, (q, sides) in enumerate(((final, (2, 2)), (coarse, (4, 4)))):
+            sampler = vs.VisionTokenSampler(hidden, hidden, [hidden] * 2, list(sides), hidden, layers).eval()
+            sampler.load_state_dict({k[len(f"vision_sampler_{g}."):]: torch.from_numpy(v) for k, v in sd.items()
+                                     if k.startswith(f"vision_sampler_{g}.")}, strict=True)
+            lat, masks = Bare().rearrange_vision_tower_features_inference(feats, q, sizes)
+            nq = q * q
+            ctx = feats[0].mean(1).view(bs, 1, 1, -1).expand(-1, nq, 1, -1).flatten(0, 1)
+            qry = torch.from_numpy(sd["vision_query"])[g].view(1, 1, 1, -1).expand(bs, nq, -1, -1).flatten(0, 1)
+            o = sampler(qry, ctx, *lat, *masks).view(bs, nq, hidden)
+            if q != final:                                                     # cambrian_arch.py:1107-1131
+                o = o.permute(0, 2, 1).contiguous().view(bs, -1, q, q)
+                o = F.interpolate(o.float(), size=(final, final), mode="bilinear", align_corners=False)
+                o = o.permute(0, 2, 3, 1).contiguous().flatten(1, 2)
+            outs.append(o)
+        ref = torch.cat(outs, -1)
+    got = sva_oracle.sva_frames_groups(sd, tower, sizes, (final, coarse), final, layers)   # 16 heads, as the reference
+    assert got.shape == ref.shape == (bs, final * final, 2 * hidden)
+    assert float((got - ref).abs().max()) <= 5e-5
