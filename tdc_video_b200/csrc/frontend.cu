@@ -73,28 +73,33 @@ __global__ void __launch_bounds__(256) pool_static_queries_kernel(const __nv_bfl
   const int end = static_cast<int>((static_cast<long long>(i + 1) * L + num_query - 1) / num_query);
   const float inv = 1.0f / static_cast<float>(end - start);
   const __nv_bfloat16* frame = xv + static_cast<long long>(c) * side * side * d;
-  for (int j = threadIdx.x; j < d / 4; j += 256) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // 8 columns (one 16-byte vector) per thread; the bin's tokens are independent loads, all issued before the adds
+  for (int j = threadIdx.x; j < d / 8; j += 256) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
     for (int u = start; u < end; ++u) {
       const int g = u / (side + 1), col = u % (side + 1);
-      float4 v;
       if (col < side) {
-        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(frame + static_cast<long long>(g * side + col) * d) + j);
-        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
-        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-        v = make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(frame + static_cast<long long>(g * side + col) * d) + j);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+          acc[2 * e] += __low2float(v);
+          acc[2 * e + 1] += __high2float(v);
+        }
       } else {
         // the reference pools the model-dtype (bf16) copy of the parameter
-        const float4 nl = __ldg(reinterpret_cast<const float4*>(newline) + j);
-        v = make_float4(__bfloat162float(__float2bfloat16_rn(nl.x)), __bfloat162float(__float2bfloat16_rn(nl.y)),
-                        __bfloat162float(__float2bfloat16_rn(nl.z)), __bfloat162float(__float2bfloat16_rn(nl.w)));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += __bfloat162float(__float2bfloat16_rn(__ldg(newline + j * 8 + e)));
       }
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    uint2 pk;
-    pk.x = pack_bf16x2(acc.x * inv, acc.y * inv);
-    pk.y = pack_bf16x2(acc.z * inv, acc.w * inv);
-    reinterpret_cast<uint2*>(out + (static_cast<long long>(c) * num_query + i) * d)[j] = pk;
+    uint4 pk;
+    pk.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+    pk.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+    pk.z = pack_bf16x2(acc[4] * inv, acc[5] * inv);
+    pk.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+    reinterpret_cast<uint4*>(out + (static_cast<long long>(c) * num_query + i) * d)[j] = pk;
   }
 }
 
@@ -259,8 +264,8 @@ int matvec_bias_launch(const __nv_bfloat16* w, const float* x, const float* b, f
 int pool_static_queries_launch(const __nv_bfloat16* xv, const float* newline, int chunks, int side, int d,
                                int num_query, __nv_bfloat16* out, cudaStream_t stream, const char** err) {
   if (chunks <= 0) return TDC_OK;
-  if (d % 4 != 0) {
-    if (err) *err = "pool_static_queries: d must be a multiple of 4";
+  if (d % 8 != 0) {
+    if (err) *err = "pool_static_queries: d must be a multiple of 8";
     return TDC_EINVAL;
   }
   pool_static_queries_kernel<<<static_cast<unsigned>(chunks * num_query), 256, 0, stream>>>(xv, newline, side, d,

@@ -560,6 +560,14 @@ int launch_variant(const GemmProblem& p, cudaStream_t stream, const char** err) 
   if (n_group > num_n_tiles) n_group = num_n_tiles;
   const int groups = (num_n_tiles + n_group - 1) / n_group;
   n_group = (num_n_tiles + groups - 1) / groups;
+  // Wave alignment (dev knob TDC_GEMM_ALIGN_WAVES=1): with N-fastest order inside a group, the `clusters` tiles in
+  // flight cover clusters / n_group A row-panels; when that is not an integer a panel's tiles are split over two
+  // waves and the panel is fetched from DRAM twice (the K/V output streaming through L2 evicts it in between).
+  // Rounding the persistent grid down to a multiple of n_group (74 -> 72 pairs for 18-tile groups) keeps every
+  // panel inside one wave at the price of 2 idle pairs.
+  static const bool align_waves = [] { const char* e = getenv("TDC_GEMM_ALIGN_WAVES"); return e != nullptr && atoi(e) == 1; }();
+  if (align_waves && groups > 1 && n_group >= 8 && clusters > n_group && tiles > 4 * clusters)
+    clusters = clusters / n_group * n_group;
 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(clusters * CG * MC));
