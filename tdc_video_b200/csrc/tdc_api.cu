@@ -611,7 +611,7 @@ struct FramesWorkspace {
 };
 
 FramesWorkspace carve_frames(const tdc_handle* h, uint8_t* base, long long n_chunks, long long rows, long long nb,
-                             int Tv, int Ta, int side, int K, int T) {
+                             int Tv, int Ta, int side, int K, int T, bool fold = false) {
   const tdc_config& c = h->cfg;
   const size_t D = c.d_enc, H = c.hidden, N = static_cast<size_t>(nb);
   Carver cv{base};
@@ -621,11 +621,18 @@ FramesWorkspace carve_frames(const tdc_handle* h, uint8_t* base, long long n_chu
   w.l0_sets = cv.take<float>(static_cast<size_t>(n_chunks) * (K + T) * H);
   w.fin = cv.take<__nv_bfloat16>(N * Tv * c.d_frame_in);
   w.pmid = cv.take<__nv_bfloat16>(N * Tv * D);
-  w.xv = cv.take<__nv_bfloat16>(N * Tv * D);
   w.ain = cv.take<__nv_bfloat16>(N * Ta * std::max(c.d_audio, 8));
-  w.xa = cv.take<__nv_bfloat16>(N * Ta * D);
-  w.pooled = cv.take<__nv_bfloat16>(N * K * D);
-  w.kv = cv.take<__nv_bfloat16>((N * (Tv + Ta) + side) * 2 * H * h->n_cross);
+  // K/V slabs of the dynamic pass.  With folded weights the projected visual / audio tokens and the pooled queries
+  // are needed by the key-frame pass only, which is over before the first K/V GEMM runs: they alias the slabs
+  // (1.5 MB per item saved -> larger row batches in the same workspace).  With fold = 0 the dynamic pass reads xv / xa
+  // as the INPUT of the K/V GEMMs, so they get their own space behind the slabs.
+  const size_t kv_elems = (N * (Tv + Ta) + side) * 2 * H * h->n_cross;
+  const size_t alias_elems = N * Tv * D + N * Ta * D + N * K * D;
+  w.kv = cv.take<__nv_bfloat16>(std::max(kv_elems, fold ? alias_elems : size_t{0}));
+  __nv_bfloat16* alias_base = fold ? w.kv : cv.take<__nv_bfloat16>(alias_elems);
+  w.xv = alias_base;
+  w.xa = alias_base ? alias_base + N * Tv * D : nullptr;
+  w.pooled = alias_base ? alias_base + N * Tv * D + N * Ta * D : nullptr;
   w.qws = base ? base + cv.off : nullptr;
   // the Q-Former's own buffers: carve_workspace with L = 0 drops its enc / kv parts
   cv.off += carve_workspace(h, nullptr, nb, 0, K, T, false, true).bytes;
@@ -974,7 +981,8 @@ int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* worksp
   // internal batch: the largest item count (<= 65535, the gather grid) whose buffers fit the workspace
   const long long most = std::max<long long>(a.rows, a.n_chunks);
   long long nb = std::min<long long>(most, 65535);
-  auto need = [&](long long n) { return carve_frames(h, nullptr, a.n_chunks, a.rows, n, fc.Tv, fc.Ta, fc.side, fc.K, fc.T).bytes; };
+  const bool fold = a.fold != 0;
+  auto need = [&](long long n) { return carve_frames(h, nullptr, a.n_chunks, a.rows, n, fc.Tv, fc.Ta, fc.side, fc.K, fc.T, fold).bytes; };
   if (need(nb) > workspace_bytes) {
     const size_t fixed = need(0), one = need(1) - fixed;
     if (workspace_bytes < fixed + one) return fail(h, TDC_EWORKSPACE, "workspace too small for a single row; see tdc_frames_workspace_bytes");
@@ -983,7 +991,7 @@ int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* worksp
     if (nb <= 0) return fail(h, TDC_EWORKSPACE, "workspace too small for a single row; see tdc_frames_workspace_bytes");
   }
   FramesWorkspace w = carve_frames(h, static_cast<uint8_t*>(workspace), a.n_chunks, a.rows, nb, fc.Tv, fc.Ta, fc.side,
-                                   fc.K, fc.T);
+                                   fc.K, fc.T, fold);
 
   // pass 1: key frames (queries of every chunk, pass-through tokens)
   if (a.n_chunks > 0 && (!fc.learned || a.static_out != nullptr))

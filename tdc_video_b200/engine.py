@@ -50,6 +50,10 @@ class QFormerEngine:
                              ln_eps=ln_eps, d_frame_in=d_frame_in, d_audio=d_audio)
         env_cap = os.environ.get("TDC_MAX_WORKSPACE_GB")   # dev knob: smaller workspace = smaller internal row batches
         self.max_workspace_bytes = int(float(env_cap) * (1 << 30)) if env_cap else int(max_workspace_bytes)
+        # the upstream entry keeps more per row (tower features, gelu(mm_projector.0)): 11 GB = 1800-row batches at
+        # the north-star shapes, the same batch the 8 GB cap gives the tokens entry (profiles/r02_frames_row_batch.txt)
+        self.max_frames_workspace_bytes = int(float(env_cap) * (1 << 30)) if env_cap else max(int(max_workspace_bytes),
+                                                                                              11 << 30)
         self._ws: Optional[torch.Tensor] = None
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -232,7 +236,7 @@ class QFormerEngine:
         most = max(rows, n_chunks, 1)
         need = int(self.lib.tdc_frames_workspace_bytes(self._h, n_chunks, rows, most, Tv, Ta, K, T))
         floor = int(self.lib.tdc_frames_workspace_bytes(self._h, n_chunks, rows, 1, Tv, Ta, K, T))
-        want = max(min(need, self.max_workspace_bytes), floor)
+        want = max(min(need, self.max_frames_workspace_bytes), floor)
         if self._ws is None or self._ws.numel() < want:
             self._ws = None
             self._ws = torch.empty(want, dtype=torch.uint8, device=self.device)

@@ -167,11 +167,11 @@ def test_frames_small_workspace_and_host_streaming_give_the_same_bits():
     _, comp_nd = eng.compress_frames(f_dev, sf, rf, rc, audio=a_dev, layer0_dedup=False, want_static=False)
     assert torch.equal(comp, comp_nd)               # layer-0 de-duplication is bit-identical
     small = int(eng.lib.tdc_frames_workspace_bytes(eng._h, p.num_chunks, p.num_rows, 5, 144, 50, 16, 0))
-    eng._ws, eng.max_workspace_bytes = None, small
+    eng._ws, eng.max_frames_workspace_bytes = None, small
     st2, comp2 = eng.compress_frames(f_dev, sf, rf, rc, audio=a_dev)
     assert eng._ws.numel() == small
     assert torch.equal(st, st2) and torch.equal(comp, comp2)
-    eng._ws, eng.max_workspace_bytes = None, 8 << 30
+    eng._ws, eng.max_frames_workspace_bytes = None, 11 << 30
     chunk_start = p.static_frames
     out_host = torch.empty((p.num_rows, 16, 3584), dtype=torch.bfloat16, pin_memory=True)
     st3 = torch.empty_like(st)
