@@ -33,6 +33,39 @@ def _stream(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def plan_chunk_ranges(n_chunks: int, chunks_per_batch: int, taper_tail: bool = True):
+    """Ranges of consecutive chunks for the host-streaming entries: full batches, then — because the stream is
+    transfer-bound and the caller waits for the LAST range's compute + read-back after the last byte has arrived — a
+    tapered tail (half of what is left, again and again, down to 1/8 of a batch)."""
+    bounds, c0 = [], 0
+    cb = max(1, min(int(chunks_per_batch), int(n_chunks)))
+    while n_chunks - c0 > cb:
+        bounds.append((c0, c0 + cb))
+        c0 += cb
+    while taper_tail and n_chunks - c0 > max(cb // 8, 1):
+        step = (n_chunks - c0) // 2
+        bounds.append((c0, c0 + step))
+        c0 += step
+    if c0 < n_chunks:
+        bounds.append((c0, n_chunks))
+    return bounds
+
+
+def range_plan(chunk_start, chunk_len, a: int, b: int, keep_static: bool = True):
+    """Integer plan of chunks [a, b) relative to the first frame of the range: (first frame, end frame,
+    static_frames [b-a], row_frames [rows], row_chunk [rows]) — int32 numpy arrays for tdc_compress_frames."""
+    import numpy as np
+    cs = np.asarray(chunk_start, dtype=np.int64)
+    cl = np.asarray(chunk_len, dtype=np.int64)
+    f0, f1 = int(cs[a]), int(cs[b - 1] + cl[b - 1])
+    st = (cs[a:b] - f0).astype(np.int32)
+    first = 1 if keep_static else 0
+    rows = [np.arange(s + first, s + n, dtype=np.int32) for s, n in zip(st, cl[a:b])]
+    rf = np.concatenate(rows) if rows and sum(len(r) for r in rows) else np.zeros(0, np.int32)
+    rck = np.repeat(np.arange(b - a, dtype=np.int32), (cl[a:b] - first).astype(np.int64))
+    return f0, f1, st, rf, rck
+
+
 class QFormerEngine:
     """Owns one `tdc_handle` (re-packed bf16 weights on one GPU) and a growable workspace."""
 
@@ -321,16 +354,7 @@ class QFormerEngine:
         cur = torch.cuda.current_stream(dev)
         if not hasattr(self, "_h2d_stream"):
             self._h2d_stream, self._d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        # ranges of chunks; taper the tail so that the last range's compute + read-back is short
-        bounds, c0 = [], 0
-        cb = max(1, min(chunks_per_batch, Cn))
-        while Cn - c0 > cb:
-            bounds.append((c0, c0 + cb)); c0 += cb
-        while Cn - c0 > max(cb // 8, 1):
-            step = (Cn - c0) // 2
-            bounds.append((c0, c0 + step)); c0 += step
-        if c0 < Cn:
-            bounds.append((c0, Cn))
+        bounds = plan_chunk_ranges(Cn, chunks_per_batch)
         max_frames = max(int(cs[b - 1] + cl[b - 1] - cs[a]) for a, b in bounds)
         Tv, d_in = frames_host.shape[1], frames_host.shape[2]
         stage_f = [torch.empty((max_frames, Tv, d_in), dtype=torch.bfloat16, device=dev) for _ in range(2)]
@@ -344,15 +368,7 @@ class QFormerEngine:
         self._h2d_stream.wait_stream(cur)
         for i, (a, b) in enumerate(bounds):
             sb = i % 2
-            f0, f1 = int(cs[a]), int(cs[b - 1] + cl[b - 1])
-            # integer plan of the range, relative to its first frame
-            st = (cs[a:b] - f0).astype(np.int32)
-            if keep_static:
-                rf = np.concatenate([np.arange(s + 1, s + n, dtype=np.int32) for s, n in zip(st, cl[a:b])]) \
-                    if int(rows_per_chunk[a:b].sum()) else np.zeros(0, np.int32)
-            else:
-                rf = np.concatenate([np.arange(s, s + n, dtype=np.int32) for s, n in zip(st, cl[a:b])])
-            rck = np.repeat(np.arange(b - a, dtype=np.int32), rows_per_chunk[a:b])
+            f0, f1, st, rf, rck = range_plan(cs, cl, a, b, keep_static)
             with torch.cuda.stream(self._h2d_stream):
                 if i >= 2:
                     self._h2d_stream.wait_event(compute_done[sb])
