@@ -100,10 +100,10 @@ def frames_flops(w, tv=144, d_in=1024, d_audio=768):
     return model, executed, (F_ - 1) * kv_exec_row
 
 
-def measured_traffic_per_row():
+def measured_traffic_per_row(name="kv_gemm_traffic.json"):
     """DRAM bytes per row of the KV-projection GEMM from the committed ncu --set full capture
-    (profiles/kv_gemm_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum over the rows of that launch)."""
-    p = os.path.join(ROOT, "profiles", "kv_gemm_traffic.json")
+    (profiles/kv_gemm_traffic*.json: dram__bytes_read.sum + dram__bytes_write.sum over the rows of that launch)."""
+    p = os.path.join(ROOT, "profiles", name)
     if not os.path.exists(p):
         return None
     d = json.load(open(p))
@@ -347,6 +347,7 @@ def main():
     ap.add_argument("--unfolded-steps", type=int, default=3, help="frames entry, N = 1: timed steps of the fold = 0 sub-record")
     ap.add_argument("--no-qformer-only", action="store_true", help="skip the round-1 style sub-record (N = 1 only)")
     ap.add_argument("--e2e-chunks-per-batch", type=int, default=300, help="chunks per H2D range of compress_frames_host")
+    ap.add_argument("--e2e-no-head-taper", action="store_true", help="dev: first H2D range as large as the others")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.segments:
@@ -609,7 +610,7 @@ def bench_frames(args, w, ctx):
     if not args.no_e2e:
         out_host = torch.empty((rows, K, d), dtype=torch.bfloat16, pin_memory=pinned)
         kw = dict(input_ids=None if ids_dev is None else ids_dev.cpu(), num_query=K, fold=fold, static_out=static_out,
-                  chunks_per_batch=args.e2e_chunks_per_batch)
+                  chunks_per_batch=args.e2e_chunks_per_batch, taper_head=not args.e2e_no_head_taper)
         if world > 1:
             kw["out_device"] = torch.empty((rows, K, d), dtype=torch.bfloat16, device=dev)
             if gathered is None:
@@ -660,7 +661,14 @@ def bench_frames(args, w, ctx):
         "roofline": {"kernel": "tdc_gemm_kernel (cross-attn K/V projection of all 6 layers, N=9216: visual tokens "
                                "K=3584 + audio tokens K=768 per row batch)",
                      "bound": "tensor", "achieved": kv_achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": (kv_achieved / peaks["tflops_sustained"]) if kv_achieved else None, "traffic": None,
+                     "frac": (kv_achieved / peaks["tflops_sustained"]) if kv_achieved else None,
+                     "traffic": (measured_traffic_per_row("kv_gemm_traffic_r02.json") * rows * args.steps / max(kv_n // 2, 1))
+                     if (fold and measured_traffic_per_row("kv_gemm_traffic_r02.json")) else None,
+                     "traffic_note": "DRAM read + write of ONE visual-token K/V launch = ncu bytes per row "
+                                     "(profiles/kv_gemm_traffic_r02.json) x rows per launch; the audio-token launches "
+                                     "(K = 768, ~8 % of the class time) are not in this figure; algorithmic = "
+                                     "rows*144*(3584 + 9216)*2 B + the 66 MB weight",
+                     "algorithmic_bytes": rows * args.steps / max(kv_n // 2, 1) * 144 * (d + 2 * H * N_CROSS) * 2 + 2 * H * N_CROSS * d * 2,
                      "flops": "EXECUTED by these launches (folded weights): rows x (2*144*3584 + 2*50*768) x 9216",
                      "peak_source": peaks["source"] + " bf16_tflops_sustained", "launches": kv_n,
                      "avg_launch_ms": kv_ms / max(kv_n, 1), "share_of_step": kv_ms / (ms_step * args.steps)},

@@ -139,7 +139,9 @@ tdc_gemm_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], kNumEpilogueWarps);
-      for (int q = 0; q < 4; ++q) mbar_init(&stats_bar[s * 4 + q], 1);  // one expect_tx arrive per use
+      // cluster: one expect_tx arrive per use, the partials arrive as transaction bytes (st.async);
+      // single CTA: plain shared-memory stores, every thread of the quadrant's two warps arrives
+      for (int q = 0; q < 4; ++q) mbar_init(&stats_bar[s * 4 + q], cluster_size > 1 ? 1 : 64);
     }
     fence_mbar_init();
   }
@@ -230,7 +232,8 @@ tdc_gemm_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const bool row_ok = row < m;
       uint64_t* sbar = &stats_bar[acc * 4 + quad];
       // the partials of this (tile, quad): 2 halves x CL CTAs x 32 rows x 8 bytes, announced once per use
-      if (half == 0 && lane == 0) mbar_arrive_expect_tx(sbar, static_cast<uint32_t>(2 * cluster_size * 32 * 8));
+      if (cluster_size > 1 && half == 0 && lane == 0)
+        mbar_arrive_expect_tx(sbar, static_cast<uint32_t>(2 * cluster_size * 32 * 8));
       // The residual does not depend on the MMAs: fetch this thread's row piece (kHalfCols fp32, one 128-byte line
       // per 32 columns) while the mainloop of this tile is still running; two 32-column chunks stay in flight.
       const float4* rrow = reinterpret_cast<const float4*>(ln.resid + static_cast<long long>(row) * ln.ldr + col_base);
@@ -286,7 +289,12 @@ tdc_gemm_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
         // every CTA of the cluster (this one included) receives this thread's partial
         float2* slot = stats + ((acc * kMaxCluster + cta) * 2 + half) * kBlockM + row_in_tile;
-        for (int dst = 0; dst < cluster_size; ++dst) st_async_f32x2(slot, sbar, static_cast<uint32_t>(dst), mean_l, m2_l);
+        if (cluster_size > 1) {
+          for (int dst = 0; dst < cluster_size; ++dst) st_async_f32x2(slot, sbar, static_cast<uint32_t>(dst), mean_l, m2_l);
+        } else {  // narrow rows (N <= BLOCK_N): the tile lives in one CTA, no distributed shared memory involved
+          *slot = make_float2(mean_l, m2_l);
+          mbar_arrive(sbar);
+        }
       }
       // ---- combine the 2 * CL partials of this thread's row
       mbar_wait(sbar, acc_phase);

@@ -33,12 +33,18 @@ def _stream(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def plan_chunk_ranges(n_chunks: int, chunks_per_batch: int, taper_tail: bool = True):
-    """Ranges of consecutive chunks for the host-streaming entries: full batches, then — because the stream is
-    transfer-bound and the caller waits for the LAST range's compute + read-back after the last byte has arrived — a
-    tapered tail (half of what is left, again and again, down to 1/8 of a batch)."""
+def plan_chunk_ranges(n_chunks: int, chunks_per_batch: int, taper_tail: bool = True, taper_head: bool = False):
+    """Ranges of consecutive chunks for the host-streaming entries: full batches, then — because the caller waits
+    for the LAST range's compute + read-back after the last byte has arrived — a tapered tail (half of what is left,
+    again and again, down to 1/8 of a batch).  `taper_head`: the first ranges grow 1/8, 1/4, 1/2 of a batch, so
+    that the copy nothing can overlap with (the first one) is short."""
     bounds, c0 = [], 0
     cb = max(1, min(int(chunks_per_batch), int(n_chunks)))
+    if taper_head and cb >= 16:
+        for frac in (8, 4, 2):
+            if n_chunks - c0 > 2 * cb:
+                bounds.append((c0, c0 + cb // frac))
+                c0 += cb // frac
     while n_chunks - c0 > cb:
         bounds.append((c0, c0 + cb))
         c0 += cb
@@ -328,7 +334,7 @@ class QFormerEngine:
                              chunk_len, out_host: Optional[torch.Tensor] = None, *, input_ids=None, num_query: int = 16,
                              learned_queries: bool = False, fold: bool = True, keep_static: bool = True,
                              static_out: Optional[torch.Tensor] = None, chunks_per_batch: int = 256,
-                             out_device: Optional[torch.Tensor] = None) -> torch.Tensor:
+                             out_device: Optional[torch.Tensor] = None, taper_head: bool = True) -> torch.Tensor:
         """`compress_frames` for tower outputs that live in (pinned) HOST memory, in video order: contiguous
         ranges of whole chunks are streamed to the GPU on a copy stream while the previous range computes, each
         range's compressed tokens go back to `out_host` on a third stream.  This is the end-to-end entry of the
@@ -354,7 +360,7 @@ class QFormerEngine:
         cur = torch.cuda.current_stream(dev)
         if not hasattr(self, "_h2d_stream"):
             self._h2d_stream, self._d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        bounds = plan_chunk_ranges(Cn, chunks_per_batch)
+        bounds = plan_chunk_ranges(Cn, chunks_per_batch, taper_head=taper_head)
         max_frames = max(int(cs[b - 1] + cl[b - 1] - cs[a]) for a, b in bounds)
         Tv, d_in = frames_host.shape[1], frames_host.shape[2]
         stage_f = [torch.empty((max_frames, Tv, d_in), dtype=torch.bfloat16, device=dev) for _ in range(2)]

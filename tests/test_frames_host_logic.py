@@ -12,9 +12,12 @@ from tdc_video_b200.compressor import plan_chunks  # noqa: E402
 from tdc_video_b200.engine import plan_chunk_ranges, range_plan  # noqa: E402
 
 
-@pytest.mark.parametrize("n,cb", [(1, 4), (7, 4), (3600, 300), (3600, 256), (100, 1000), (9, 1)])
-def test_chunk_ranges_cover_everything_once(n, cb):
-    b = plan_chunk_ranges(n, cb)
+@pytest.mark.parametrize("head", [False, True])
+@pytest.mark.parametrize("n,cb", [(1, 4), (7, 4), (3600, 300), (3600, 256), (100, 1000), (9, 1), (700, 300)])
+def test_chunk_ranges_cover_everything_once(n, cb, head):
+    b = plan_chunk_ranges(n, cb, taper_head=head)
+    if head and n > 2 * cb and cb >= 16:
+        assert b[0][1] - b[0][0] == cb // 8
     assert b[0][0] == 0 and b[-1][1] == n
     assert all(x[1] == y[0] for x, y in zip(b, b[1:])) and all(lo < hi for lo, hi in b)
     assert max(hi - lo for lo, hi in b) <= max(1, min(cb, n))
