@@ -346,7 +346,7 @@ def main():
     ap.add_argument("--no-fold", action="store_true", help="frames entry: run every projection as the reference orders them")
     ap.add_argument("--unfolded-steps", type=int, default=3, help="frames entry, N = 1: timed steps of the fold = 0 sub-record")
     ap.add_argument("--no-qformer-only", action="store_true", help="skip the round-1 style sub-record (N = 1 only)")
-    ap.add_argument("--e2e-chunks-per-batch", type=int, default=300, help="chunks per H2D range of compress_frames_host")
+    ap.add_argument("--e2e-chunks-per-batch", type=int, default=600, help="chunks per H2D range of compress_frames_host")
     ap.add_argument("--e2e-no-head-taper", action="store_true", help="dev: first H2D range as large as the others")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
