@@ -165,7 +165,7 @@ typedef struct tdc_frames_args {
   const int32_t* static_frames;  /* [n_chunks] frame index of every chunk's key frame */
   const int32_t* row_frames;     /* [rows]     frame index of every dynamic frame */
   const int32_t* row_chunk;      /* [rows]     chunk of every row (its query set) */
-  const int64_t* input_ids;      /* [1, num_text] prompt shared by all rows, or NULL */
+  const int64_t* input_ids;      /* [n_prompts, num_text] BERT ids of the prompt(s), or NULL */
   int32_t n_frames, n_chunks, rows;
   int32_t visual_tokens;         /* Tv (144) */
   int32_t audio_tokens;          /* Ta (50) or 0 */
@@ -181,6 +181,8 @@ typedef struct tdc_frames_args {
                                   * 1: computed per row */
   void* static_out;              /* [n_chunks, side*(side+1) + Ta, d_out] the key frames as they pass through, or NULL */
   void* out;                     /* [rows, K, d_out] compressed tokens */
+  const int32_t* chunk_prompt;   /* [n_chunks] prompt (row of input_ids) of every chunk — several videos with their own
+                                  * questions in one call (the eval loops run many clips concurrently); NULL: prompt 0 */
 } tdc_frames_args;
 
 /* Workspace for tdc_compress_frames processing `batch` rows (and key frames) at a time; any size from

@@ -52,7 +52,7 @@ class TdcFramesArgs(C.Structure):
         ("audio_tokens", C.c_int32), ("num_query", C.c_int32), ("num_text", C.c_int32),
         ("learned_queries", C.c_int32), ("fold", C.c_int32), ("multicast", C.c_int32), ("out_dtype", C.c_int32),
         ("no_layer0_dedup", C.c_int32),
-        ("static_out", C.c_void_p), ("out", C.c_void_p),
+        ("static_out", C.c_void_p), ("out", C.c_void_p), ("chunk_prompt", C.c_void_p),
     ]
 
 

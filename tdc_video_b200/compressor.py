@@ -200,6 +200,55 @@ class TDCCompressor(nn.Module):
                     dtype=dtype)
         return self._assemble(prep, comp, max_visual_len)
 
+    @torch.no_grad()
+    def compress_videos_from_towers(self, videos: Sequence[dict], fold: bool = True) -> List[torch.Tensor]:
+        """Several videos through ONE tdc_compress_frames call (the eval loops run many clips concurrently; BASELINE
+        config 5): every item is a dict with the arguments of `compress_video_from_towers` — `tower_features`,
+        `segment_sizes`, optional `input_ids` (each video its own question), `audio_frames`, `max_visual_len`.
+        Videos must agree on having a prompt / audio and on the prompt length (group them otherwise).
+        Returns one token sequence per video, equal bit for bit to the per-video calls."""
+        if not videos:
+            return []
+        if self.training:
+            raise RuntimeError("TDCCompressor is inference-only (eval mode)")
+        if not self.add_static:
+            raise NotImplementedError("compress_videos_from_towers keeps the key frames (add_static=True)")
+        plans, frame_base, chunk_base = [], [0], [0]
+        for v in videos:
+            if sum(int(x) for x in v["segment_sizes"]) != v["tower_features"].shape[0]:
+                raise ValueError("segment_sizes must sum to the number of frames")
+            plans.append(plan_chunks(v["segment_sizes"], True))
+            frame_base.append(frame_base[-1] + v["tower_features"].shape[0])
+            chunk_base.append(chunk_base[-1] + plans[-1].num_chunks)
+        use_text = self.text_input and videos[0].get("input_ids") is not None and videos[0]["input_ids"].numel() > 0
+        use_audio = videos[0].get("audio_frames") is not None
+        for v in videos:
+            if (v.get("audio_frames") is not None) != use_audio:
+                raise ValueError("all videos of one call must agree on audio")
+            if use_text and (v.get("input_ids") is None or v["input_ids"].numel() != videos[0]["input_ids"].numel()):
+                raise ValueError("all videos of one call must have prompts of the same length")
+        t0 = videos[0]["tower_features"]
+        dev = t0.device
+        dtype = t0.dtype if t0.dtype in (torch.bfloat16, torch.float16) else torch.float32
+        frames = torch.cat([v["tower_features"] for v in videos], dim=0)
+        audio = torch.cat([v["audio_frames"].to(dev) for v in videos], dim=0) if use_audio else None
+        i32 = lambda arrs: torch.from_numpy(np.concatenate(arrs).astype(np.int32))
+        sf = i32([p.static_frames + fb for p, fb in zip(plans, frame_base)])
+        rf = i32([p.row_frames + fb for p, fb in zip(plans, frame_base)])
+        rc = i32([p.row_chunk + cb for p, cb in zip(plans, chunk_base)])
+        ids = torch.cat([v["input_ids"].reshape(1, -1) for v in videos], dim=0) if use_text else None
+        cp = i32([np.full(p.num_chunks, i) for i, p in enumerate(plans)]) if use_text else None
+        static_tok, comp = self._frames_engine().compress_frames(
+            frames, sf, rf, rc, audio=audio, input_ids=ids, num_query=self.context_token_num,
+            learned_queries=self.query_type == "learned", fold=fold, want_static=True, out_dtype=dtype, chunk_prompt=cp)
+        outs, r0 = [], 0
+        for i, (p, v) in enumerate(zip(plans, videos)):
+            prep = dict(plan=p, static_tok=static_tok[chunk_base[i]:chunk_base[i + 1]], L=static_tok.shape[1],
+                        d=self.llm_hidden_size, dev=dev, dtype=dtype)
+            outs.append(self._assemble(prep, comp[r0:r0 + p.num_rows], v.get("max_visual_len")))
+            r0 += p.num_rows
+        return outs
+
     def build_queries(self, static_visual: torch.Tensor):
         """[C, Lv, d] visual-only key frames -> query sets [C, K, hidden] fp32 (cambrian_arch.py:1629-1640).
         The key frame is taken BEFORE the audio tokens are appended (:1609 vs :1614)."""

@@ -219,6 +219,13 @@ __global__ void __launch_bounds__(256) resize_tokens_bilinear_kernel(const void*
   }
 }
 
+// out[r] = a[b[r]]  (row -> chunk -> prompt)
+__global__ void compose_index_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int32_t* __restrict__ out,
+                                     long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[b[i]];
+}
+
 int launched(const char** err) {
   const cudaError_t rc = cudaGetLastError();
   if (rc != cudaSuccess) {
@@ -296,6 +303,13 @@ int resize_tokens_bilinear_launch(const void* in, int in_dtype, int bs, int s_in
   }
   resize_tokens_bilinear_kernel<<<static_cast<unsigned>((toks + 7) / 8), 256, 0, stream>>>(in, in_dtype, s_in, s_out, d,
                                                                                           out, out_dtype, toks);
+  return launched(err);
+}
+
+int compose_index_launch(const int32_t* a, const int32_t* b, int32_t* out, long long n, cudaStream_t stream,
+                         const char** err) {
+  if (n <= 0) return TDC_OK;
+  compose_index_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(a, b, out, n);
   return launched(err);
 }
 

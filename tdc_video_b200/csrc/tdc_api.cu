@@ -597,6 +597,7 @@ struct FramesWorkspace {
   // whole call
   float* q_sets;       // [n_chunks, K, H] fp32 (Avg_pool queries, one set per chunk)
   int32_t* zero_map;   // [max(rows, n_chunks)] zeros: "every row uses set 0" (shared prompt / learned queries)
+  int32_t* row_prompt; // [rows] prompt of every row when several videos share the call
   float* l0_sets;      // [n_chunks, K + T, H] fp32: state after layer 0's self-attention block, one per chunk
   // per batch of nb items (nb key frames in the static pass, nb rows in the dynamic pass)
   __nv_bfloat16* fin;     // [nb*Tv, d_in]   gathered tower features
@@ -618,6 +619,7 @@ FramesWorkspace carve_frames(const tdc_handle* h, uint8_t* base, long long n_chu
   FramesWorkspace w{};
   w.q_sets = cv.take<float>(static_cast<size_t>(n_chunks) * K * H);
   w.zero_map = cv.take<int32_t>(static_cast<size_t>(std::max(rows, n_chunks)));
+  w.row_prompt = cv.take<int32_t>(static_cast<size_t>(rows));
   w.l0_sets = cv.take<float>(static_cast<size_t>(n_chunks) * (K + T) * H);
   w.fin = cv.take<__nv_bfloat16>(N * Tv * c.d_frame_in);
   w.pmid = cv.take<__nv_bfloat16>(N * Tv * D);
@@ -1005,12 +1007,19 @@ int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* worksp
   if (zero_map && cudaMemsetAsync(w.zero_map, 0, static_cast<size_t>(std::max(a.rows, a.n_chunks)) * sizeof(int32_t),
                                   s) != cudaSuccess)
     return fail(h, TDC_ECUDA, "cudaMemsetAsync failed");
+  // several prompts: row -> chunk -> prompt (the chunk's video)
+  const bool multi_prompt = fc.T > 0 && a.chunk_prompt != nullptr;
+  if (multi_prompt) {
+    const char* err = nullptr;
+    const int rc = compose_index_launch(a.chunk_prompt, a.row_chunk, w.row_prompt, a.rows, s, &err);
+    if (rc != TDC_OK) return fail(h, rc, err ? err : "compose_index failed");
+  }
   ForwardCall f{};
   f.query_embeds = fc.learned ? h->query_tokens : w.q_sets;
   f.query_dtype = TDC_F32;
   f.query_set = fc.learned ? w.zero_map : a.row_chunk;
   f.input_ids = fc.T > 0 ? a.input_ids : nullptr;
-  f.text_set = fc.T > 0 ? w.zero_map : nullptr;
+  f.text_set = fc.T > 0 ? (multi_prompt ? w.row_prompt : w.zero_map) : nullptr;
   f.enc = nullptr; f.enc_dtype = TDC_BF16; f.kv_len = nullptr;
   f.rows = a.rows; f.L = fc.Tv + fc.Ta + fc.side; f.K = fc.K; f.T = fc.T;
   f.out = a.out; f.out_dtype = a.out_dtype; f.compress = true; f.multicast = a.multicast != 0;
@@ -1018,10 +1027,13 @@ int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* worksp
   // to and including layer 0's self-attention block — compute it once per chunk (once in total for learned queries)
   // and broadcast it.  Same kernels on the same values: bit-identical to the per-row computation.
   if (!a.no_layer0_dedup && c.layers > 1) {
-    const long long n_sets = fc.learned ? 1 : a.n_chunks;
+    // one state per chunk — or ONE in total when nothing distinguishes the chunks (learned queries, one prompt)
+    const bool per_chunk = !fc.learned || multi_prompt;
+    const long long n_sets = per_chunk ? a.n_chunks : 1;
     ForwardCall p = f;
     p.rows = n_sets;
-    p.query_set = nullptr;            // "row" i of the pre-pass uses query set i
+    p.query_set = fc.learned ? w.zero_map : nullptr;   // "row" i of the pre-pass uses query set i (set 0 if learned)
+    if (multi_prompt) p.text_set = a.chunk_prompt;      // ... and its chunk's prompt
     p.l0_out = w.l0_sets;
     Workspace qw0{};
     for (long long s0 = 0; s0 < n_sets; s0 += nb) {
@@ -1031,7 +1043,7 @@ int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* worksp
       if (rc != TDC_OK) return rc;
     }
     f.l0_sets = w.l0_sets;
-    f.l0_map = fc.learned ? nullptr : a.row_chunk;
+    f.l0_map = per_chunk ? a.row_chunk : nullptr;
   }
   for (long long r0 = 0; r0 < a.rows; r0 += nb) {
     const int rc = frames_dynamic_batch(h, fc, f, w, r0, std::min<long long>(nb, a.rows - r0), s);

@@ -111,6 +111,9 @@ int assemble_static_launch(const __nv_bfloat16* xv, const __nv_bfloat16* xa, con
 // bilinear (align_corners = False) resize of a token grid, token-major: [bs, s_in^2, d] -> [bs, s_out^2, d]
 int resize_tokens_bilinear_launch(const void* in, int in_dtype, int bs, int s_in, int s_out, int d, void* out,
                                   int out_dtype, cudaStream_t stream, const char** err);
+// out[i] = a[b[i]]
+int compose_index_launch(const int32_t* a, const int32_t* b, int32_t* out, long long n, cudaStream_t stream,
+                         const char** err);
 // rows [row0, row0 + count) of each of `slabs` matrices [*, width] (slab_stride elements apart) = src[slab] as bf16
 int broadcast_rows_launch(const float* src, int width, int slabs, __nv_bfloat16* dst, long long slab_stride,
                           long long row0, int count, cudaStream_t stream, const char** err);

@@ -285,12 +285,15 @@ class QFormerEngine:
                         row_chunk: torch.Tensor, *, audio: Optional[torch.Tensor] = None,
                         input_ids: Optional[torch.Tensor] = None, num_query: int = 16, learned_queries: bool = False,
                         fold: bool = True, want_static: bool = True, out_dtype=torch.bfloat16,
-                        multicast_ptr: Optional[int] = None, layer0_dedup: bool = True):
+                        multicast_ptr: Optional[int] = None, layer0_dedup: bool = True,
+                        chunk_prompt: Optional[torch.Tensor] = None):
         """The TDC stage from the towers' outputs (tdc_compress_frames): mm_projector, image_newline, audio_proj,
         query build, Q-Former, vision_proj + L2-normalise for all chunks of a video in one call.
 
         frames [n_frames, Tv, d_frame_in] bf16 (input of mm_projector), audio [n_frames, Ta, d_audio] bf16 or None,
         static_frames [C] / row_frames [R] / row_chunk [R] int32 (see compressor.plan_chunks).
+        input_ids [1, T] (one prompt for all rows) or [P, T] with chunk_prompt [C] int32 (prompt of every chunk:
+        several videos with their own questions in one call).
         Returns (static_out [C, side*(side+1)+Ta, d] or None, compressed [R, K, d])."""
         if self.cfg.d_frame_in <= 0:
             raise RuntimeError("engine was created without d_frame_in: no upstream entry")
@@ -312,7 +315,14 @@ class QFormerEngine:
         rc_ = row_chunk.to(dev, torch.int32).contiguous()
         C_, R = int(sf.numel()), int(rf.numel())
         T = 0 if input_ids is None else int(input_ids.shape[-1])
-        ids = None if T == 0 else input_ids.reshape(1, T).to(dev, torch.int64).contiguous()
+        ids = None if T == 0 else input_ids.reshape(-1, T).to(dev, torch.int64).contiguous()
+        cp = None
+        if T > 0 and chunk_prompt is not None:
+            cp = chunk_prompt.to(dev, torch.int32).contiguous()
+            if cp.numel() != C_:
+                raise ValueError("chunk_prompt needs one entry per chunk")
+        elif T > 0 and ids.shape[0] != 1:
+            raise ValueError("several prompts need chunk_prompt")
         side = int(round(Tv ** 0.5))
         d = self.cfg.d_out
         static_out = torch.empty((C_, side * (side + 1) + Ta, d), dtype=out_dtype, device=dev) if want_static else None
@@ -324,7 +334,8 @@ class QFormerEngine:
                           rc_.data_ptr(), None if ids is None else ids.data_ptr(), n_frames, C_, R, Tv, Ta, num_query,
                           T, int(learned_queries), int(fold), int(multicast_ptr is not None), _DTYPES[out_dtype],
                           int(not layer0_dedup), None if static_out is None else static_out.data_ptr(),
-                          int(multicast_ptr) if multicast_ptr is not None else out.data_ptr())
+                          int(multicast_ptr) if multicast_ptr is not None else out.data_ptr(),
+                          None if cp is None else cp.data_ptr())
         with torch.cuda.device(dev):
             rc = self.lib.tdc_compress_frames(self._h, C.byref(a), _ptr(ws), ws.numel(), _stream(dev))
         check(rc, self._h, "tdc_compress_frames")

@@ -194,3 +194,61 @@ def test_frames_entry_errors():
     with pytest.raises(RuntimeError):
         QFormerEngine(hidden=128, heads=2, intermediate=256, layers=2, cross_freq=2, d_enc=64, d_out=64).compress_frames(
             torch.zeros(2, 16, 32, device="cuda", dtype=torch.bfloat16), z, z + 1, z)
+
+
+def test_frames_entry_edge_cases():
+    """Only single-frame chunks (no rows at all), learned queries with a prompt (layer-0 state computed once in
+    total), fp16 outputs, and a non-square token grid rejected loudly."""
+    from tdc_video_b200 import TdcError
+    geom, sd, frames, aud, _ = _full_problem(14, 6, 1, audio=True, T=5)
+    eng = _engine(geom, sd, 1024, True, T=5)
+    f_dev, a_dev = torch.from_numpy(frames).cuda().bfloat16(), torch.from_numpy(aud).cuda().bfloat16()
+    ids = torch.randint(1000, 30000, (1, 5), generator=torch.Generator().manual_seed(5))
+    # (1) six chunks of one frame: key frames pass through, nothing to compress
+    p, sf, rf, rc = _plan([1] * 6)
+    assert p.num_rows == 0
+    st, comp = eng.compress_frames(f_dev, sf, rf, rc, audio=a_dev, input_ids=ids.cuda(), out_dtype=torch.float32)
+    ref_st, ref_comp = _oracle_frames(sd, geom, frames, aud, [1] * 6, 16, ids)
+    assert comp.shape == (0, 16, 3584) and ref_comp.shape[0] == 0
+    _ok(st, ref_st, "key frames only")
+    # (2) learned queries + prompt, chunks of 4 and 2 frames, fp16 output
+    from oracle import frames_oracle
+    p, sf, rf, rc = _plan([4, 2])
+    st16, comp16 = eng.compress_frames(f_dev, sf, rf, rc, audio=a_dev, input_ids=ids.cuda(), learned_queries=True,
+                                       out_dtype=torch.float16)
+    x, a = torch.from_numpy(frames).bfloat16().float(), torch.from_numpy(aud).bfloat16().float()
+    ref_st, ref_comp = frames_oracle.frames_stage(sd, geom, x, a, p.static_frames, p.chunk_len, 16, ids,
+                                                  learned_queries=True)
+    assert comp16.dtype == torch.float16 and tuple(comp16.shape) == (4, 16, 3584)
+    _ok(st16, ref_st, "learned/text static fp16")
+    _ok(comp16, ref_comp, "learned/text compressed fp16")
+    _, comp_nd = eng.compress_frames(f_dev, sf, rf, rc, audio=a_dev, input_ids=ids.cuda(), learned_queries=True,
+                                     out_dtype=torch.float16, layer0_dedup=False, want_static=False)
+    assert torch.equal(comp16, comp_nd)
+    # (3) 140 visual tokens are not a square grid
+    with pytest.raises(TdcError):
+        eng.compress_frames(f_dev[:, :140].contiguous(), sf, rf, rc, audio=a_dev)
+
+
+def test_several_videos_with_their_own_prompts_in_one_call():
+    """compress_videos_from_towers: three clips of different lengths, each with its own question, through ONE
+    tdc_compress_frames call (chunk -> prompt map, layer-0 state per chunk) == the per-video calls, bit for bit."""
+    from tdc_video_b200.compressor import TDCCompressor
+    from tdc_video_b200.qformer import QFormerConfig
+    torch.manual_seed(3)
+    cfg = QFormerConfig(vocab_size=64, hidden_size=128, num_hidden_layers=4, num_attention_heads=2,
+                        intermediate_size=256, max_position_embeddings=16)
+    for query_type in ("Avg_pool", "learned"):
+        comp = TDCCompressor(96, context_token_num=8, query_type=query_type, audio_input=True, qformer_config=cfg,
+                             mm_input_size=40).cuda().eval()
+        vids = []
+        for n, sizes in ((13, [5, 1, 7]), (9, [9]), (4, [2, 2])):
+            vids.append(dict(tower_features=torch.randn(n, 16, 40, device="cuda", dtype=torch.bfloat16),
+                             segment_sizes=sizes, input_ids=torch.randint(1, 64, (1, 5), device="cuda"),
+                             audio_frames=torch.randn(n, 6, 768, device="cuda", dtype=torch.bfloat16),
+                             max_visual_len=None))
+        together = comp.compress_videos_from_towers(vids)
+        for v, got in zip(vids, together):
+            alone = comp.compress_video_from_towers(v["tower_features"], v["segment_sizes"], input_ids=v["input_ids"],
+                                                    audio_frames=v["audio_frames"])
+            assert torch.equal(got, alone), query_type
