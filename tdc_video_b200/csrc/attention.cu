@@ -101,8 +101,8 @@ __global__ void __launch_bounds__(128, 4) tdc_attention_kernel(AttentionArgs a) 
     qb_[0] = y0.x; qb_[1] = y0.y; qb_[2] = y0.z; qb_[3] = y0.w; qb_[4] = y1.x; qb_[5] = y1.y; qb_[6] = y1.z; qb_[7] = y1.w;
   }
 
-  const __nv_bfloat16* kbase = a.k + h * 64 + c * 8;
-  const __nv_bfloat16* vbase = a.v + h * 64 + g * 8;
+  const __nv_bfloat16* kbase = a.k + h * a.k_head_stride + c * 8;
+  const __nv_bfloat16* vbase = a.v + h * a.v_head_stride + g * 8;
   if (!kTwoSeg) {  // fold the row's first KV token into the base pointers
     const long long first = a.kv_base1 + static_cast<long long>(r) * a.kv_seg1;
     kbase += first * a.ldk;

@@ -606,9 +606,11 @@ int gemm_launch(const GemmProblem& p, cudaStream_t stream, const char** err) {
     if (err) *err = "gemm: bf16 output pitch must be a multiple of 8 elements";
     return TDC_EINVAL;
   }
-  if (p.slab_cols < 0 || (p.slab_cols > 0 && ((p.slab_cols % 128) != 0 || (p.n % p.slab_cols) != 0 ||
+  // a store box is 128 bytes wide: 64 bf16 or 32 fp32 columns; slabs must be whole boxes
+  const int box_cols = p.mode == EPI_BIAS_F32 ? 32 : 64;
+  if (p.slab_cols < 0 || (p.slab_cols > 0 && ((p.slab_cols % box_cols) != 0 || (p.n % p.slab_cols) != 0 ||
                                               (p.slab_stride % 8) != 0))) {
-    if (err) *err = "gemm: slab_cols must be a multiple of 128 dividing N, slab_stride a multiple of 8";
+    if (err) *err = "gemm: slab_cols must be a multiple of the 128-byte store box dividing N, slab_stride a multiple of 8";
     return TDC_EINVAL;
   }
   if (p.mode < 0 || p.mode > EPI_BIAS_F32) {

@@ -372,13 +372,14 @@ bool fused_ln_enabled(int n) {
   return !off && gemm_ln_supported(n);
 }
 
-// Where the cross-attention K/V of a row batch live: one dense [slab_rows, 2H] (K | V) matrix per cross layer
-// (`slab_stride` elements apart, row pitch `pitch`).  Row r's KV tokens: seg1 tokens at slab row r*seg1 + t, then
+// Where the cross-attention K/V of a row batch live: one dense [slab_rows, 64] matrix per (cross layer, K | V, head),
+// `head_stride` elements apart in the column order of the fused K/V weight (layer, K | V, head) — a (row, head) pair
+// of an attention launch streams one contiguous run of 128-byte lines, and every TMA store box of the K/V GEMM's
+// epilogue (32 tokens x 64 columns) is one contiguous 4 KB write.  Row r's KV tokens: seg1 tokens at slab row r*seg1 + t, then
 // seg2 tokens at base2 + r*seg2 + t, then seg3 tokens at base3 + t shared by ALL rows (the image_newline tokens).
 struct KvView {
   const __nv_bfloat16* base = nullptr;
-  long long slab_stride = 0, pitch = 0;
-  bool slabs = true;   // false: interleaved [rows*L, kvw] layout (odd head counts), seg2 = seg3 = 0
+  long long head_stride = 0;   // = slab rows * 64
   int seg1 = 0, seg2 = 0, seg3 = 0;
   long long base2 = 0, base3 = 0;
 };
@@ -473,10 +474,10 @@ int qformer_layers(tdc_handle* h, const ForwardCall& f, long long row0, long lon
       TDC_TRY(gemm(h, TDC_K_QUERY_GEMM, s, w.h_bf16, H, lw.w_cq, H, lw.b_cq, w.qc, H, MQ, H, H, EPI_BIAS_BF16, &err));
       AttentionArgs a;
       a.q = w.qc; a.out = w.ctx; a.ldq = H; a.ldo = H;
-      a.k = kv.slabs ? kv.base + static_cast<size_t>(lw.cross_index) * kv.slab_stride
-                     : kv.base + static_cast<size_t>(lw.cross_index) * 2 * H;
-      a.v = a.k + H;
-      a.ldk = a.ldv = kv.pitch;
+      a.k = kv.base + static_cast<size_t>(lw.cross_index) * 2 * c.heads * kv.head_stride;
+      a.v = a.k + static_cast<size_t>(c.heads) * kv.head_stride;
+      a.ldk = a.ldv = 64;
+      a.k_head_stride = a.v_head_stride = kv.head_stride;
       a.rows = static_cast<int>(rows); a.heads = c.heads; a.nq = K;
       a.q_seg1 = K; a.q_seg2 = 0;
       a.kv_seg1 = kv.seg1; a.kv_seg2 = kv.seg2; a.kv_seg3 = kv.seg3;
@@ -536,19 +537,15 @@ int forward_batch(tdc_handle* h, const ForwardCall& f, long long row0, long long
   }
   const int kvw = 2 * H * h->n_cross;  // K/V columns per KV token over all cross layers
 
-  // every cross layer's K and V for every KV token of every row: the dominant GEMM.  Output layout:
-  // one dense [rows*L, 2H] (K | V) matrix per cross layer, so that a layer's attention launch streams a
-  // contiguous region (633 KB per row) instead of 3 KB pieces at an 18 KB stride.  2H is a multiple of
-  // 128 whenever heads is even; odd head counts fall back to the interleaved [rows*L, kvw] layout.
+  // every cross layer's K and V for every KV token of every row: the dominant GEMM.  Output layout: one dense
+  // [rows*L, 64] matrix per (layer, K | V, head) — see KvView.
   KvView kv;
   kv.base = w.kv;
-  kv.slabs = ((2 * H) % 128) == 0;
-  kv.slab_stride = kv.slabs ? rows * L * 2ll * H : 0;
-  kv.pitch = kv.slabs ? 2 * H : kvw;
+  kv.head_stride = rows * L * 64ll;
   kv.seg1 = L;
   if (h->n_cross > 0)
-    TDC_TRY(gemm(h, TDC_K_KV_GEMM, s, enc, c.d_enc, h->w_ckv, c.d_enc, h->b_ckv, w.kv, kv.pitch, rows * L, kvw,
-                 c.d_enc, EPI_BIAS_BF16, &err, kv.slabs ? 2 * H : 0, kv.slab_stride));
+    TDC_TRY(gemm(h, TDC_K_KV_GEMM, s, enc, c.d_enc, h->w_ckv, c.d_enc, h->b_ckv, w.kv, 64, rows * L, kvw,
+                 c.d_enc, EPI_BIAS_BF16, &err, 64, kv.head_stride));
   return qformer_layers(h, f, row0, rows, w, kv, f.kv_len ? f.kv_len + row0 : nullptr, s);
 }
 
@@ -606,7 +603,7 @@ struct FramesWorkspace {
   __nv_bfloat16* ain;     // [nb*Ta, d_audio]
   __nv_bfloat16* xa;      // [nb*Ta, d]
   __nv_bfloat16* pooled;  // [nb*K, d]
-  __nv_bfloat16* kv;      // n_cross slabs of [nb*(Tv+Ta) + side, 2H]
+  __nv_bfloat16* kv;      // n_cross * 2 * heads slabs of [nb*(Tv+Ta) + side, 64]
   uint8_t* qws;           // Q-Former workspace of nb rows (carve_workspace without the kv / enc parts)
   size_t bytes;
 };
@@ -703,11 +700,10 @@ int frames_dynamic_batch(tdc_handle* h, const FramesCall& fc, const ForwardCall&
   const char* err = nullptr;
   KvView kv;
   kv.base = w.kv;
-  kv.pitch = 2 * H;
   kv.seg1 = Tv; kv.seg2 = Ta; kv.seg3 = fc.side;
   kv.base2 = rb * Tv;
   kv.base3 = rb * (Tv + Ta);
-  kv.slab_stride = (rb * (Tv + Ta) + fc.side) * 2ll * H;
+  kv.head_stride = (rb * (Tv + Ta) + fc.side) * 64ll;
   {
     KernelScope ks(h, TDC_K_FRONTEND, s);
     TDC_TRY(gather_blocks_launch(a.frames, a.row_frames + r0, w.fin, rb, static_cast<long long>(Tv) * c.d_frame_in * 2,
@@ -718,11 +714,11 @@ int frames_dynamic_batch(tdc_handle* h, const FramesCall& fc, const ForwardCall&
   if (h->n_cross > 0) {
     if (a.fold) {
       TDC_TRY(frames_gemm(h, TDC_K_KV_GEMM, s, w.pmid, D, h->w_kvf, h->b_kvf, w.kv, rb * Tv, kvw, EPI_BIAS_BF16, &err,
-                          2 * H, kv.slab_stride, 2 * H));
+                          64, kv.head_stride, 64));
     } else {
       TDC_TRY(frames_gemm(h, TDC_K_FRONTEND, s, w.pmid, D, h->w_p2, h->b_p2, w.xv, rb * Tv, D, EPI_BIAS_BF16, &err));
       TDC_TRY(frames_gemm(h, TDC_K_KV_GEMM, s, w.xv, D, h->w_ckv, h->b_ckv, w.kv, rb * Tv, kvw, EPI_BIAS_BF16, &err,
-                          2 * H, kv.slab_stride, 2 * H));
+                          64, kv.head_stride, 64));
     }
     if (Ta > 0) {
       {
@@ -730,19 +726,19 @@ int frames_dynamic_batch(tdc_handle* h, const FramesCall& fc, const ForwardCall&
         TDC_TRY(gather_blocks_launch(a.audio, a.row_frames + r0, w.ain, rb, static_cast<long long>(Ta) * c.d_audio * 2,
                                      s, &err));
       }
-      __nv_bfloat16* kv_aud = w.kv + kv.base2 * 2 * H;
+      __nv_bfloat16* kv_aud = w.kv + kv.base2 * 64;
       if (a.fold) {
         TDC_TRY(frames_gemm(h, TDC_K_KV_GEMM, s, w.ain, c.d_audio, h->w_kva, h->b_kva, kv_aud, rb * Ta, kvw,
-                            EPI_BIAS_BF16, &err, 2 * H, kv.slab_stride, 2 * H));
+                            EPI_BIAS_BF16, &err, 64, kv.head_stride, 64));
       } else {
         TDC_TRY(frames_gemm(h, TDC_K_FRONTEND, s, w.ain, c.d_audio, h->w_ap, h->b_ap, w.xa, rb * Ta, D, EPI_BIAS_BF16,
                             &err));
         TDC_TRY(frames_gemm(h, TDC_K_KV_GEMM, s, w.xa, D, h->w_ckv, h->b_ckv, kv_aud, rb * Ta, kvw, EPI_BIAS_BF16, &err,
-                            2 * H, kv.slab_stride, 2 * H));
+                            64, kv.head_stride, 64));
       }
     }
     KernelScope ks(h, TDC_K_FRONTEND, s);
-    TDC_TRY(broadcast_rows_launch(h->kv_newline, 2 * H, h->n_cross, w.kv, kv.slab_stride, kv.base3, fc.side, s, &err));
+    TDC_TRY(broadcast_rows_launch(h->kv_newline, 64, kvw / 64, w.kv, kv.head_stride, kv.base3, fc.side, s, &err));
   }
   Workspace qw = carve_workspace(h, w.qws, rb, 0, fc.K, fc.T, false, true);
   return qformer_layers(h, f, r0, rb, qw, kv, nullptr, s);
@@ -951,7 +947,6 @@ int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* worksp
     return fail(h, TDC_ESTATE, "tdc_compress_frames needs d_frame_in > 0 and the mm_projector / image_newline / "
                                "query_proj / vision_proj weights");
   if (c.d_enc != c.d_out) return fail(h, TDC_EINVAL, "tdc_compress_frames needs d_enc == d_out (the LLM width)");
-  if ((2 * c.hidden) % 128 != 0) return fail(h, TDC_EINVAL, "tdc_compress_frames needs an even number of heads");
   FramesCall fc{};
   fc.a = args;
   fc.Tv = a.visual_tokens; fc.Ta = a.audio_tokens; fc.K = a.num_query; fc.T = a.num_text;

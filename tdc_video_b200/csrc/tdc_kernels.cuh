@@ -22,6 +22,10 @@ struct AttentionArgs {
   const __nv_bfloat16* v = nullptr;
   __nv_bfloat16* out = nullptr;  // same token addressing as q
   long long ldq = 0, ldk = 0, ldv = 0, ldo = 0;
+  // elements between the K (V) of consecutive heads: 64 = heads side by side inside a token row (the default), or a
+  // whole [tokens, 64] matrix per head (the Q-Former's cross-attention K/V slabs: a (row, head) pair streams one
+  // contiguous run of 128-byte lines)
+  long long k_head_stride = 64, v_head_stride = 64;
   int rows = 0, heads = 0;
   int nq = 0;  // queries per row (= q_seg1 + q_seg2)
   int q_seg1 = 0, q_seg2 = 0;
