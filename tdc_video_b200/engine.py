@@ -382,17 +382,28 @@ class QFormerEngine:
         h2d_done = [torch.cuda.Event() for _ in range(2)]
         compute_done = [torch.cuda.Event() for _ in range(2)]
         ids_dev = None if input_ids is None else input_ids.to(dev)
+        # the integer plans of all ranges go up in ONE small copy before the pipeline starts (a pageable copy per
+        # range would block the host behind that range's frame copy)
+        plans = [range_plan(cs, cl, a, b, keep_static) for a, b in bounds]
+        flat = np.concatenate([np.concatenate(p[2:5]) for p in plans]) if plans else np.zeros(0, np.int32)
+        flat_dev = torch.from_numpy(flat.astype(np.int32)).to(dev)
+        offs, o = [], 0
+        for p in plans:
+            n_st, n_rf = len(p[2]), len(p[3])
+            offs.append((o, o + n_st, o + n_st + n_rf, o + n_st + 2 * n_rf))
+            o += n_st + 2 * n_rf
         self._h2d_stream.wait_stream(cur)
         for i, (a, b) in enumerate(bounds):
             sb = i % 2
-            f0, f1, st, rf, rck = range_plan(cs, cl, a, b, keep_static)
+            f0, f1 = plans[i][0], plans[i][1]
+            o0, o1, o2, o3 = offs[i]
+            plan_dev = [flat_dev[o0:o1], flat_dev[o1:o2], flat_dev[o2:o3]]
             with torch.cuda.stream(self._h2d_stream):
                 if i >= 2:
                     self._h2d_stream.wait_event(compute_done[sb])
                 stage_f[sb][: f1 - f0].copy_(frames_host[f0:f1], non_blocking=True)
                 if stage_a is not None:
                     stage_a[sb][: f1 - f0].copy_(audio_host[f0:f1], non_blocking=True)
-                plan_dev = [torch.from_numpy(x).to(dev, non_blocking=True) for x in (st, rf, rck)]
                 h2d_done[sb].record(self._h2d_stream)
             cur.wait_event(h2d_done[sb])
             s_out, comp = self.compress_frames(stage_f[sb][: f1 - f0], plan_dev[0], plan_dev[1], plan_dev[2],
@@ -400,8 +411,6 @@ class QFormerEngine:
                                                input_ids=ids_dev, num_query=K, learned_queries=learned_queries,
                                                fold=fold, want_static=static_out is not None,
                                                out_dtype=out_host.dtype)
-            for t in plan_dev:
-                t.record_stream(cur)
             r0, r1 = int(row_base[a]), int(row_base[b])
             if static_out is not None:
                 static_out[a:b].copy_(s_out)
