@@ -183,6 +183,10 @@ typedef struct tdc_frames_args {
   void* out;                     /* [rows, K, d_out] compressed tokens */
   const int32_t* chunk_prompt;   /* [n_chunks] prompt (row of input_ids) of every chunk — several videos with their own
                                   * questions in one call (the eval loops run many clips concurrently); NULL: prompt 0 */
+  int32_t n_prompts;             /* rows of input_ids (0 or 1: a single prompt).  All index arrays are DEVICE data the
+                                  * library cannot validate on the host: frame / chunk / prompt indices are clamped into
+                                  * range on the device instead of being trusted */
+  int32_t reserved0;
 } tdc_frames_args;
 
 /* Workspace for tdc_compress_frames processing `batch` rows (and key frames) at a time; any size from

@@ -16,9 +16,10 @@ namespace {
 
 // dst block i = src block idx[i]; a block is `vecs` 16-byte vectors (one frame's tokens).
 __global__ void __launch_bounds__(256) gather_blocks_kernel(const uint4* __restrict__ src, const int32_t* __restrict__ idx,
-                                                            uint4* __restrict__ dst, long long vecs) {
+                                                            uint4* __restrict__ dst, long long vecs, int n_src) {
   const long long item = blockIdx.y;
-  const uint4* s = src + static_cast<long long>(idx[item]) * vecs;
+  const int i = min(max(idx[item], 0), n_src - 1);   // a bad index must not read outside the caller's buffer
+  const uint4* s = src + static_cast<long long>(i) * vecs;
   uint4* d = dst + item * vecs;
   for (long long v = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; v < vecs;
        v += static_cast<long long>(gridDim.x) * 256)
@@ -221,9 +222,9 @@ __global__ void __launch_bounds__(256) resize_tokens_bilinear_kernel(const void*
 
 // out[r] = a[b[r]]  (row -> chunk -> prompt)
 __global__ void compose_index_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int32_t* __restrict__ out,
-                                     long long n) {
+                                     long long n, int n_a) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = a[b[i]];
+  if (i < n) out[i] = a[min(max(b[i], 0), n_a - 1)];
 }
 
 int launched(const char** err) {
@@ -238,7 +239,7 @@ int launched(const char** err) {
 }  // namespace
 
 int gather_blocks_launch(const void* src, const int32_t* idx, void* dst, long long items, long long block_bytes,
-                         cudaStream_t stream, const char** err) {
+                         int n_src, cudaStream_t stream, const char** err) {
   if (items <= 0) return TDC_OK;
   if (block_bytes % 16 != 0 || items > 65535) {
     if (err) *err = "gather_blocks: block size must be a multiple of 16 bytes and at most 65535 blocks per call";
@@ -248,7 +249,7 @@ int gather_blocks_launch(const void* src, const int32_t* idx, void* dst, long lo
   int bx = static_cast<int>((vecs + 255) / 256);
   if (bx > 32) bx = 32;
   gather_blocks_kernel<<<dim3(bx, static_cast<unsigned>(items)), 256, 0, stream>>>(
-      static_cast<const uint4*>(src), idx, static_cast<uint4*>(dst), vecs);
+      static_cast<const uint4*>(src), idx, static_cast<uint4*>(dst), vecs, n_src);
   return launched(err);
 }
 
@@ -306,10 +307,10 @@ int resize_tokens_bilinear_launch(const void* in, int in_dtype, int bs, int s_in
   return launched(err);
 }
 
-int compose_index_launch(const int32_t* a, const int32_t* b, int32_t* out, long long n, cudaStream_t stream,
+int compose_index_launch(const int32_t* a, int n_a, const int32_t* b, int32_t* out, long long n, cudaStream_t stream,
                          const char** err) {
   if (n <= 0) return TDC_OK;
-  compose_index_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(a, b, out, n);
+  compose_index_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(a, b, out, n, n_a);
   return launched(err);
 }
 

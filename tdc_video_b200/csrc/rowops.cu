@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(256) embed_layernorm_kernel(EmbedArgs a) {
   float4 v[kMaxVec];
   long long dst_row;
   if (i < a.num_query) {
-    const long long set = a.query_set ? a.query_set[r] : r;
+    long long set = a.query_set ? a.query_set[r] : r;
+    if (a.num_query_sets > 0) set = set < 0 ? 0 : (set >= a.num_query_sets ? a.num_query_sets - 1 : set);
     const long long base4 = (set * a.num_query + i) * (width / 4);
 #pragma unroll
     for (int j = 0; j < kMaxVec; ++j)
@@ -139,7 +140,8 @@ __global__ void __launch_bounds__(256) embed_layernorm_kernel(EmbedArgs a) {
     dst_row = static_cast<long long>(r) * a.num_query + i;
   } else {
     const int t = i - a.num_query;
-    const long long set = a.text_set ? a.text_set[r] : r;
+    long long set = a.text_set ? a.text_set[r] : r;
+    if (a.num_text_sets > 0) set = set < 0 ? 0 : (set >= a.num_text_sets ? a.num_text_sets - 1 : set);
     long long id = a.input_ids[set * a.num_text + t];
     id = id < 0 ? 0 : (id >= a.vocab ? a.vocab - 1 : id);
     const float4* we = reinterpret_cast<const float4*>(a.word_emb + id * width);
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
 // h (slab layout of `rows` rows) <- sets[set_map[r]] (set-major [set][K + T][hidden], fp32): the layer-0 state
 // computed once per (query set, prompt) broadcast to every row that shares it; also writes the bf16 copy.
 __global__ void __launch_bounds__(256) broadcast_sets_kernel(const float* __restrict__ sets,
-                                                             const int32_t* __restrict__ set_map, int rows,
+                                                             const int32_t* __restrict__ set_map, int num_sets, int rows,
                                                              int num_query, int num_text, int hidden,
                                                              float* __restrict__ h_f32,
                                                              __nv_bfloat16* __restrict__ h_bf16) {
@@ -181,7 +183,8 @@ __global__ void __launch_bounds__(256) broadcast_sets_kernel(const float* __rest
   if (tok >= static_cast<long long>(rows) * n) return;
   const int lane = threadIdx.x & 31;
   const int r = static_cast<int>(tok / n), i = static_cast<int>(tok % n);
-  const long long set = set_map ? set_map[r] : 0;
+  long long set = set_map ? set_map[r] : 0;
+  set = set < 0 ? 0 : (set >= num_sets ? num_sets - 1 : set);
   const float4* src = reinterpret_cast<const float4*>(sets + (set * n + i) * hidden);
   const long long dst = (i < num_query) ? static_cast<long long>(r) * num_query + i
                                         : static_cast<long long>(rows) * num_query +
@@ -365,12 +368,13 @@ int gather_rows_launch(const float* h_f32, int hidden, int rows, int num_query, 
   return check_launch(err);
 }
 
-int broadcast_sets_launch(const float* sets, const int32_t* set_map, int rows, int num_query, int num_text, int hidden,
-                          float* h_f32, __nv_bfloat16* h_bf16, cudaStream_t stream, const char** err) {
+int broadcast_sets_launch(const float* sets, const int32_t* set_map, int num_sets, int rows, int num_query, int num_text,
+                          int hidden, float* h_f32, __nv_bfloat16* h_bf16, cudaStream_t stream, const char** err) {
   const long long toks = static_cast<long long>(rows) * (num_query + num_text);
   if (toks <= 0) return TDC_OK;
-  broadcast_sets_kernel<<<static_cast<unsigned>((toks + 7) / 8), 256, 0, stream>>>(sets, set_map, rows, num_query,
-                                                                                   num_text, hidden, h_f32, h_bf16);
+  broadcast_sets_kernel<<<static_cast<unsigned>((toks + 7) / 8), 256, 0, stream>>>(sets, set_map, num_sets, rows,
+                                                                                   num_query, num_text, hidden, h_f32,
+                                                                                   h_bf16);
   return check_launch(err);
 }
 

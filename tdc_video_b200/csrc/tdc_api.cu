@@ -345,6 +345,8 @@ struct ForwardCall {
                                       // state of every "row" (= one per set) set-major [rows, K + T, hidden] fp32
   const float* l0_sets = nullptr;     // main pass: start from these states instead of recomputing them per row
   const int32_t* l0_map = nullptr;    // [rows] row -> set (NULL: set 0)
+  int l0_num_sets = 1;
+  int num_query_sets = 0, num_text_sets = 0;   // > 0: device-side set indices are clamped into range
 };
 
 #define TDC_TRY(expr)                                         \
@@ -395,7 +397,8 @@ int qformer_layers(tdc_handle* h, const ForwardCall& f, long long row0, long lon
   // embeddings + LayerNorm into the [query slab | text slab] layout
   if (f.l0_sets != nullptr) {
     KernelScope ks(h, TDC_K_ROWOPS, s);
-    TDC_TRY(broadcast_sets_launch(f.l0_sets, f.l0_map ? f.l0_map + row0 : nullptr, static_cast<int>(rows), K, T, H,
+    TDC_TRY(broadcast_sets_launch(f.l0_sets, f.l0_map ? f.l0_map + row0 : nullptr, f.l0_num_sets,
+                                  static_cast<int>(rows), K, T, H,
                                   w.h_f32, w.h_bf16, s, &err));
   } else {
     EmbedArgs e;
@@ -406,6 +409,8 @@ int qformer_layers(tdc_handle* h, const ForwardCall& f, long long row0, long lon
     e.query_set = f.query_set ? f.query_set + row0 : nullptr;
     e.input_ids = (T > 0) ? (f.text_set ? f.input_ids : f.input_ids + row0 * T) : nullptr;
     e.text_set = f.text_set ? f.text_set + row0 : nullptr;
+    e.num_query_sets = f.query_set ? f.num_query_sets : 0;
+    e.num_text_sets = f.text_set ? f.num_text_sets : 0;
     e.word_emb = h->word_emb; e.pos_emb = h->pos_emb; e.vocab = c.vocab;
     e.gamma = h->ln_e_g; e.beta = h->ln_e_b; e.eps = c.ln_eps;
     e.h_f32 = w.h_f32; e.h_bf16 = w.h_bf16;
@@ -656,7 +661,7 @@ int frames_static_batch(tdc_handle* h, const FramesCall& fc, const FramesWorkspa
   {
     KernelScope ks(h, TDC_K_FRONTEND, s);
     TDC_TRY(gather_blocks_launch(a.frames, a.static_frames + c0, w.fin, cb, static_cast<long long>(Tv) * c.d_frame_in * 2,
-                                 s, &err));
+                                 a.n_frames, s, &err));
   }
   TDC_TRY(frames_gemm(h, TDC_K_FRONTEND, s, w.fin, c.d_frame_in, h->w_p0, h->b_p0, w.pmid, cb * Tv, D,
                       EPI_BIAS_GELU_BF16, &err));
@@ -674,7 +679,7 @@ int frames_static_batch(tdc_handle* h, const FramesCall& fc, const FramesWorkspa
       {
         KernelScope ks(h, TDC_K_FRONTEND, s);
         TDC_TRY(gather_blocks_launch(a.audio, a.static_frames + c0, w.ain, cb, static_cast<long long>(Ta) * c.d_audio * 2,
-                                     s, &err));
+                                     a.n_frames, s, &err));
       }
       TDC_TRY(frames_gemm(h, TDC_K_FRONTEND, s, w.ain, c.d_audio, h->w_ap, h->b_ap, w.xa, cb * Ta, D, EPI_BIAS_BF16,
                           &err));
@@ -707,7 +712,7 @@ int frames_dynamic_batch(tdc_handle* h, const FramesCall& fc, const ForwardCall&
   {
     KernelScope ks(h, TDC_K_FRONTEND, s);
     TDC_TRY(gather_blocks_launch(a.frames, a.row_frames + r0, w.fin, rb, static_cast<long long>(Tv) * c.d_frame_in * 2,
-                                 s, &err));
+                                 a.n_frames, s, &err));
   }
   TDC_TRY(frames_gemm(h, TDC_K_FRONTEND, s, w.fin, c.d_frame_in, h->w_p0, h->b_p0, w.pmid, rb * Tv, D,
                       EPI_BIAS_GELU_BF16, &err));
@@ -724,7 +729,7 @@ int frames_dynamic_batch(tdc_handle* h, const FramesCall& fc, const ForwardCall&
       {
         KernelScope ks(h, TDC_K_FRONTEND, s);
         TDC_TRY(gather_blocks_launch(a.audio, a.row_frames + r0, w.ain, rb, static_cast<long long>(Ta) * c.d_audio * 2,
-                                     s, &err));
+                                     a.n_frames, s, &err));
       }
       __nv_bfloat16* kv_aud = w.kv + kv.base2 * 64;
       if (a.fold) {
@@ -1003,10 +1008,10 @@ int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* worksp
                                   s) != cudaSuccess)
     return fail(h, TDC_ECUDA, "cudaMemsetAsync failed");
   // several prompts: row -> chunk -> prompt (the chunk's video)
-  const bool multi_prompt = fc.T > 0 && a.chunk_prompt != nullptr;
+  const bool multi_prompt = fc.T > 0 && a.chunk_prompt != nullptr && a.n_prompts > 1;
   if (multi_prompt) {
     const char* err = nullptr;
-    const int rc = compose_index_launch(a.chunk_prompt, a.row_chunk, w.row_prompt, a.rows, s, &err);
+    const int rc = compose_index_launch(a.chunk_prompt, a.n_chunks, a.row_chunk, w.row_prompt, a.rows, s, &err);
     if (rc != TDC_OK) return fail(h, rc, err ? err : "compose_index failed");
   }
   ForwardCall f{};
@@ -1018,6 +1023,8 @@ int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* worksp
   f.enc = nullptr; f.enc_dtype = TDC_BF16; f.kv_len = nullptr;
   f.rows = a.rows; f.L = fc.Tv + fc.Ta + fc.side; f.K = fc.K; f.T = fc.T;
   f.out = a.out; f.out_dtype = a.out_dtype; f.compress = true; f.multicast = a.multicast != 0;
+  f.num_query_sets = fc.learned ? 1 : a.n_chunks;
+  f.num_text_sets = std::max(a.n_prompts, 1);
   // layer-0 de-duplication: every row of a chunk has the same queries and the same prompt, hence the same state up
   // to and including layer 0's self-attention block — compute it once per chunk (once in total for learned queries)
   // and broadcast it.  Same kernels on the same values: bit-identical to the per-row computation.
@@ -1039,6 +1046,7 @@ int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* worksp
     }
     f.l0_sets = w.l0_sets;
     f.l0_map = per_chunk ? a.row_chunk : nullptr;
+    f.l0_num_sets = static_cast<int>(n_sets);
   }
   for (long long r0 = 0; r0 < a.rows; r0 += nb) {
     const int rc = frames_dynamic_batch(h, fc, f, w, r0, std::min<long long>(nb, a.rows - r0), s);

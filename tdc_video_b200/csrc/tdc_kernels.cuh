@@ -59,6 +59,7 @@ struct EmbedArgs {
   const int32_t* query_set = nullptr;  // [rows] or null
   const int64_t* input_ids = nullptr;  // [n_text_sets, T] or null
   const int32_t* text_set = nullptr;   // [rows] or null
+  int num_query_sets = 0, num_text_sets = 0;   // > 0: set indices are clamped into range (0: trusted)
   const float* word_emb = nullptr;     // [vocab, H]
   const float* pos_emb = nullptr;      // [max_pos, H]
   int vocab = 0;
@@ -76,8 +77,8 @@ int gather_rows_launch(const float* h_f32, int hidden, int rows, int num_query, 
                        void* out, int out_dtype, cudaStream_t stream, const char** err);
 
 // h (slab layout) <- sets[set_map[r]] (set-major [set][K + T][hidden] fp32; set_map NULL = set 0 for every row)
-int broadcast_sets_launch(const float* sets, const int32_t* set_map, int rows, int num_query, int num_text, int hidden,
-                          float* h_f32, __nv_bfloat16* h_bf16, cudaStream_t stream, const char** err);
+int broadcast_sets_launch(const float* sets, const int32_t* set_map, int num_sets, int rows, int num_query, int num_text,
+                          int hidden, float* h_f32, __nv_bfloat16* h_bf16, cudaStream_t stream, const char** err);
 
 // F.normalize(x, dim=-1) (eps 1e-12; tdc/cambrian_arch.py:1664-1667): x fp32 [rows, width] -> out_dtype.
 // multicast: `out` is an NVSwitch multicast address (multimem.st): every GPU of the group gets the rows.
@@ -98,8 +99,9 @@ int avg_pool_tokens_launch(const void* frames, int dtype, int n, int tokens, int
 
 // ---- upstream ("frames") entry: frontend.cu -------------------------------------------------------------
 // dst block i = src block idx[i] (blocks of block_bytes, a multiple of 16): frames gathered by role (static / dynamic)
+// (indices are clamped to [0, n_src))
 int gather_blocks_launch(const void* src, const int32_t* idx, void* dst, long long items, long long block_bytes,
-                         cudaStream_t stream, const char** err);
+                         int n_src, cudaStream_t stream, const char** err);
 int transpose_bf16_launch(const __nv_bfloat16* in, int rows, int cols, __nv_bfloat16* out, cudaStream_t stream,
                           const char** err);
 // y = W x + b (W bf16 [n, k]; x, b, y fp32) — weight folding at load time
@@ -115,8 +117,8 @@ int assemble_static_launch(const __nv_bfloat16* xv, const __nv_bfloat16* xa, con
 // bilinear (align_corners = False) resize of a token grid, token-major: [bs, s_in^2, d] -> [bs, s_out^2, d]
 int resize_tokens_bilinear_launch(const void* in, int in_dtype, int bs, int s_in, int s_out, int d, void* out,
                                   int out_dtype, cudaStream_t stream, const char** err);
-// out[i] = a[b[i]]
-int compose_index_launch(const int32_t* a, const int32_t* b, int32_t* out, long long n, cudaStream_t stream,
+// out[i] = a[clamp(b[i], 0, n_a - 1)]
+int compose_index_launch(const int32_t* a, int n_a, const int32_t* b, int32_t* out, long long n, cudaStream_t stream,
                          const char** err);
 // rows [row0, row0 + count) of each of `slabs` matrices [*, width] (slab_stride elements apart) = src[slab] as bf16
 int broadcast_rows_launch(const float* src, int width, int slabs, __nv_bfloat16* dst, long long slab_stride,

@@ -335,7 +335,7 @@ class QFormerEngine:
                           T, int(learned_queries), int(fold), int(multicast_ptr is not None), _DTYPES[out_dtype],
                           int(not layer0_dedup), None if static_out is None else static_out.data_ptr(),
                           int(multicast_ptr) if multicast_ptr is not None else out.data_ptr(),
-                          None if cp is None else cp.data_ptr())
+                          None if cp is None else cp.data_ptr(), 0 if ids is None else int(ids.shape[0]), 0)
         with torch.cuda.device(dev):
             rc = self.lib.tdc_compress_frames(self._h, C.byref(a), _ptr(ws), ws.numel(), _stream(dev))
         check(rc, self._h, "tdc_compress_frames")

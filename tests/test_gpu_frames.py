@@ -225,7 +225,14 @@ def test_frames_entry_edge_cases():
     _, comp_nd = eng.compress_frames(f_dev, sf, rf, rc, audio=a_dev, input_ids=ids.cuda(), learned_queries=True,
                                      out_dtype=torch.float16, layer0_dedup=False, want_static=False)
     assert torch.equal(comp16, comp_nd)
-    # (3) 140 visual tokens are not a square grid
+    # (3) index arrays are device data the library cannot validate: a bad frame index is clamped, not followed
+    rf_bad = rf.clone()
+    rf_bad[0] = 10 ** 6
+    _, comp_bad = eng.compress_frames(f_dev, sf, rf_bad, rc, audio=a_dev, input_ids=ids.cuda(), learned_queries=True,
+                                      out_dtype=torch.float16, want_static=False)
+    torch.cuda.synchronize()
+    assert torch.equal(comp_bad[1:], comp16[1:]) and bool(torch.isfinite(comp_bad.float()).all())
+    # (4) 140 visual tokens are not a square grid
     with pytest.raises(TdcError):
         eng.compress_frames(f_dev[:, :140].contiguous(), sf, rf, rc, audio=a_dev)
 
