@@ -255,6 +255,17 @@ int tdc_attention(const void* q, const void* k, const void* v, void* out, int64_
 int tdc_resize_tokens_bilinear(const void* in, int32_t in_dtype, int32_t bs, int32_t side_in, int32_t side_out,
                                int32_t d, void* out, int32_t out_dtype, tdc_stream_t stream);
 
+/* replaces: the window regrouping of rearrange_vision_tower_features_inference (cambrian_arch.py:624-645) — the
+ * tokens under every query of a q x q grid, window-major: in [bs, (q r)^2, d] (dtype) -> out [bs, q, q, r, r, d] bf16. */
+int tdc_window_rearrange(const void* in, int32_t in_dtype, int32_t bs, int32_t q, int32_t r, int32_t d, void* out_bf16,
+                         tdc_stream_t stream);
+
+/* replaces: queries + (stack(aggregated) * weight_mlp(...).softmax(-1).unsqueeze(-1)).sum(2) of VisionAggregationLayer
+ * (tdc/vision_sampler.py:468-474, 505-507): out = base + sum_t softmax(logits[:, :num_parts])[t] * parts[t].
+ * base, out fp32 [rows, width]; parts fp32 [num_parts, rows, width]; logits fp32 [rows, ld_logits]. */
+int tdc_combine_parts(const float* base, const float* parts, const float* logits, int32_t ld_logits, int32_t num_parts,
+                      int64_t rows, int32_t width, float* out, tdc_stream_t stream);
+
 /* out = a + b in fp32 (out_f32 and/or out_bf16 may be NULL) — the outer residual of an SVA layer (:399). */
 int tdc_residual_add(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t count,
                      tdc_stream_t stream);

@@ -111,10 +111,50 @@ def cross_attention_layer(sd, p, queries, context, latents: Sequence[torch.Tenso
     return q + residual
 
 
-def token_sampler(sd, prefix, queries, context, latents, masks, num_layers: int, num_heads: int = 16):
-    """VisionTokenSampler.forward (vision_sampler.py:560-566), joint layers."""
+def aggregation_layer(sd, p, queries, context, latents: Sequence[torch.Tensor], masks: Sequence[torch.Tensor],
+                      num_heads: int = 16) -> torch.Tensor:
+    """VisionAggregationLayer.forward (vision_sampler.py:457-517) with AggregationBlock (:138-167) and CrossAttention
+    (:61-135): one attention (or MLP for single-token windows) per tower, mixed by softmax(weight_mlp(...))."""
+    residual = queries
+    ctx = _lin(sd, p + "proj_context", context, bias=False)
+    cat = torch.cat([queries, ctx], -1)
+    if len(latents) > 1:
+        wl = _lin(sd, p + "weight_mlp.linear_2", F.gelu(_lin(sd, p + "weight_mlp.linear_1", cat, bias=False)), bias=False)
+        weight = wl.softmax(-1).unsqueeze(-1)                                    # [R, q_len, T, 1]
+    else:
+        weight = 1
+    q = _lin(sd, p + "proj_in", cat, bias=False)
+    R, q_len, hidden = q.shape
+    dh = hidden // num_heads
+    parts = []
+    for t, v in enumerate(latents):
+        a = p + f"aggregate_{t}.attention_layer."
+        if v.shape[1] > 1:
+            v = v + _t(sd[p + f"pos_embed_{t}"])[None]
+            qs = _lin(sd, a + "q_proj.1", _ln(sd, a + "q_proj.0", q), bias=False)
+            ks = _lin(sd, a + "k_proj.1", _ln(sd, a + "k_proj.0", v), bias=False)
+            vs = _lin(sd, a + "v_proj.1", _ln(sd, a + "v_proj.0", v), bias=False)
+            n_kv = ks.shape[1]
+            qh = qs.view(R, q_len, num_heads, dh).transpose(1, 2)
+            kh = ks.view(R, n_kv, num_heads, dh).transpose(1, 2)
+            vh = vs.view(R, n_kv, num_heads, dh).transpose(1, 2)
+            m = masks[t].view(R, 1, 1, -1).expand(-1, -1, q_len, -1)
+            att = F.scaled_dot_product_attention(qh, kh, vh, attn_mask=m).transpose(1, 2).reshape(R, q_len, hidden)
+            parts.append(_lin(sd, a + "o_proj", att, bias=False))
+        else:
+            parts.append(_lin(sd, a + "linear_2", F.gelu(_lin(sd, a + "linear_1", v, bias=False)), bias=False))
+    q = q + (torch.stack(parts, 2) * weight).sum(2)
+    q = _ln(sd, p + "norm", q)
+    q = _lin(sd, p + "proj_out.linear_2", F.gelu(_lin(sd, p + "proj_out.linear_1", q, bias=False)), bias=False)
+    return q + residual
+
+
+def token_sampler(sd, prefix, queries, context, latents, masks, num_layers: int, num_heads: int = 16,
+                  layer_type: str = "joint"):
+    """VisionTokenSampler.forward (vision_sampler.py:560-566): "joint" or "sep" layers (:531-559)."""
+    layer = cross_attention_layer if layer_type == "joint" else aggregation_layer
     for i in range(num_layers):
-        queries = cross_attention_layer(sd, f"{prefix}layers.{i}.", queries, context, latents, masks, num_heads)
+        queries = layer(sd, f"{prefix}layers.{i}.", queries, context, latents, masks, num_heads)
     return queries
 
 
@@ -137,7 +177,7 @@ def sva_frames_groups(sd, tower_feats: Sequence[torch.Tensor], image_sizes: Sequ
 
 
 def sva_frames(sd, tower_feats: Sequence[torch.Tensor], image_sizes: Sequence[Tuple[int, int]], query_side: int,
-               num_layers: int, num_heads: int = 16, group: int = 0) -> torch.Tensor:
+               num_layers: int, num_heads: int = 16, group: int = 0, layer_type: str = "joint") -> torch.Tensor:
     """cambrian_arch.py:1002-1053 for one query group (group 0) at final resolution: tower features
     [bs, grid_t^2, C_t] -> query features [bs, query_side^2, hidden]."""
     feats = [mm_projector_aux(sd, f"mm_projector_aux_{t}", f) for t, f in enumerate(tower_feats)]
@@ -149,5 +189,6 @@ def sva_frames(sd, tower_feats: Sequence[torch.Tensor], image_sizes: Sequence[Tu
     latents = [rearrange_windows(f, query_side) for f in feats]
     masks = [torch.cat([window_masks(image_sizes[b], int(f.shape[1] ** 0.5), query_side) for b in range(bs)], 0)
              for f in feats]
-    out = token_sampler(sd, f"vision_sampler_{group}.", queries, context, latents, masks, num_layers, num_heads)
+    out = token_sampler(sd, f"vision_sampler_{group}.", queries, context, latents, masks, num_layers, num_heads,
+                        layer_type)
     return out.view(bs, nq, hidden)

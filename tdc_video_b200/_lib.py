@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "tdc_abi_version", "tdc_create", "tdc_destroy", "tdc_last_error", "tdc_load_weights", "tdc_workspace_bytes",
     "tdc_qformer_forward", "tdc_proj_norm", "tdc_compress", "tdc_compress_multicast", "tdc_frames_workspace_bytes",
     "tdc_compress_frames", "tdc_linear", "tdc_linear_layernorm", "tdc_gelu_mlp", "tdc_avg_pool_tokens",
-    "tdc_convert", "tdc_layernorm", "tdc_attention", "tdc_residual_add", "tdc_resize_tokens_bilinear", "tdc_segment_workspace_bytes", "tdc_segment_boundaries", "tdc_set_profiling", "tdc_get_profile", "tdc_reset_profile", "tdc_launch_count",
+    "tdc_convert", "tdc_layernorm", "tdc_attention", "tdc_residual_add", "tdc_resize_tokens_bilinear", "tdc_window_rearrange", "tdc_combine_parts", "tdc_segment_workspace_bytes", "tdc_segment_boundaries", "tdc_set_profiling", "tdc_get_profile", "tdc_reset_profile", "tdc_launch_count",
 ]
 
 
@@ -92,6 +92,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.tdc_residual_add.argtypes = [vp, vp, vp, vp, i64, vp]
     lib.tdc_resize_tokens_bilinear.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32, vp]
     lib.tdc_resize_tokens_bilinear.restype = C.c_int
+    lib.tdc_window_rearrange.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
+    lib.tdc_window_rearrange.restype = C.c_int
+    lib.tdc_combine_parts.argtypes = [vp, vp, vp, i32, i32, i64, i32, vp, vp]
+    lib.tdc_combine_parts.restype = C.c_int
     for _n in ("tdc_layernorm", "tdc_attention", "tdc_residual_add"):
         getattr(lib, _n).restype = C.c_int
     lib.tdc_segment_workspace_bytes.argtypes = [i32, i64]

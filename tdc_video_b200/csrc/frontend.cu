@@ -220,6 +220,67 @@ __global__ void __launch_bounds__(256) resize_tokens_bilinear_kernel(const void*
   }
 }
 
+// Tokens under every query of a Q x Q query grid, window-major (tdc/cambrian_arch.py:624-645): in [bs, (Q r)^2, d]
+// (row-major token grid) -> out [bs, Q, Q, r, r, d] bf16.  One warp per output token.
+__global__ void __launch_bounds__(256) window_rearrange_kernel(const void* __restrict__ in, int in_dtype, int q, int r, int d,
+                                                               __nv_bfloat16* __restrict__ out, long long tokens) {
+  const long long tok = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (tok >= tokens) return;
+  const int lane = threadIdx.x & 31;
+  const int grid = q * r;
+  long long t = tok;
+  const int wx = static_cast<int>(t % r); t /= r;
+  const int wy = static_cast<int>(t % r); t /= r;
+  const int qx = static_cast<int>(t % q); t /= q;
+  const int qy = static_cast<int>(t % q); t /= q;
+  const long long src = (t * grid + (qy * r + wy)) * grid + (qx * r + wx);
+  const size_t isz = in_dtype == TDC_F32 ? 4 : 2;
+  const uint8_t* sp = static_cast<const uint8_t*>(in) + static_cast<size_t>(src) * d * isz;
+  __nv_bfloat16* dp = out + tok * d;
+  for (int j = lane; j < d / 4; j += 32) {
+    uint2 pk;
+    if (in_dtype == TDC_BF16) {
+      pk = __ldg(reinterpret_cast<const uint2*>(sp) + j);
+    } else if (in_dtype == TDC_F32) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(sp) + j);
+      pk.x = pack_bf16x2(v.x, v.y);
+      pk.y = pack_bf16x2(v.z, v.w);
+    } else {
+      const uint2 raw = __ldg(reinterpret_cast<const uint2*>(sp) + j);
+      const __half2 a = *reinterpret_cast<const __half2*>(&raw.x);
+      const __half2 b = *reinterpret_cast<const __half2*>(&raw.y);
+      pk.x = pack_bf16x2(__low2float(a), __high2float(a));
+      pk.y = pack_bf16x2(__low2float(b), __high2float(b));
+    }
+    reinterpret_cast<uint2*>(dp)[j] = pk;
+  }
+}
+
+// out[r, :] = base[r, :] + sum_t softmax(logits[r, :T])[t] * parts[t][r, :]  — VisionAggregationLayer's combination of the
+// per-tower aggregates (tdc/vision_sampler.py:468-474, 505-507).  One warp per row, T <= 8.
+__global__ void __launch_bounds__(256) combine_parts_kernel(const float* __restrict__ base, const float* __restrict__ parts,
+                                                            const float* __restrict__ logits, int ld_logits, int num_parts,
+                                                            long long rows, int width, float* __restrict__ out) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float w[8];
+  float mx = -INFINITY;
+  for (int t = 0; t < num_parts; ++t) { w[t] = logits[row * ld_logits + t]; mx = fmaxf(mx, w[t]); }
+  float sum = 0.f;
+  for (int t = 0; t < num_parts; ++t) { w[t] = expf(w[t] - mx); sum += w[t]; }
+  const float inv = 1.0f / sum;
+  for (int j = lane; j < width / 4; j += 32) {
+    float4 acc = reinterpret_cast<const float4*>(base + row * width)[j];
+    for (int t = 0; t < num_parts; ++t) {
+      const float4 p = reinterpret_cast<const float4*>(parts + (static_cast<long long>(t) * rows + row) * width)[j];
+      const float wt = w[t] * inv;
+      acc.x = fmaf(wt, p.x, acc.x); acc.y = fmaf(wt, p.y, acc.y); acc.z = fmaf(wt, p.z, acc.z); acc.w = fmaf(wt, p.w, acc.w);
+    }
+    reinterpret_cast<float4*>(out + row * width)[j] = acc;
+  }
+}
+
 // out[r] = a[b[r]]  (row -> chunk -> prompt)
 __global__ void compose_index_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int32_t* __restrict__ out,
                                      long long n, int n_a) {
@@ -304,6 +365,30 @@ int resize_tokens_bilinear_launch(const void* in, int in_dtype, int bs, int s_in
   }
   resize_tokens_bilinear_kernel<<<static_cast<unsigned>((toks + 7) / 8), 256, 0, stream>>>(in, in_dtype, s_in, s_out, d,
                                                                                           out, out_dtype, toks);
+  return launched(err);
+}
+
+int window_rearrange_launch(const void* in, int in_dtype, int bs, int q, int r, int d, __nv_bfloat16* out,
+                            cudaStream_t stream, const char** err) {
+  const long long toks = static_cast<long long>(bs) * q * q * r * r;
+  if (toks <= 0) return TDC_OK;
+  if (d % 4 != 0) {
+    if (err) *err = "window_rearrange: d must be a multiple of 4";
+    return TDC_EINVAL;
+  }
+  window_rearrange_kernel<<<static_cast<unsigned>((toks + 7) / 8), 256, 0, stream>>>(in, in_dtype, q, r, d, out, toks);
+  return launched(err);
+}
+
+int combine_parts_launch(const float* base, const float* parts, const float* logits, int ld_logits, int num_parts,
+                         long long rows, int width, float* out, cudaStream_t stream, const char** err) {
+  if (rows <= 0) return TDC_OK;
+  if (num_parts < 1 || num_parts > 8 || width % 4 != 0) {
+    if (err) *err = "combine_parts: 1..8 parts, width a multiple of 4";
+    return TDC_EINVAL;
+  }
+  combine_parts_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(base, parts, logits, ld_logits, num_parts,
+                                                                                 rows, width, out);
   return launched(err);
 }
 

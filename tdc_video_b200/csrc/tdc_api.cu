@@ -1185,6 +1185,34 @@ int tdc_resize_tokens_bilinear(const void* in, int32_t in_dtype, int32_t bs, int
   return rc;
 }
 
+int tdc_window_rearrange(const void* in, int32_t in_dtype, int32_t bs, int32_t q, int32_t r, int32_t d, void* out_bf16,
+                         tdc_stream_t stream) {
+  if (bs == 0) return TDC_OK;
+  if (in == nullptr || out_bf16 == nullptr || bs < 0 || q <= 0 || r <= 0 || in_dtype < TDC_BF16 || in_dtype > TDC_F32) {
+    g_create_error = "tdc_window_rearrange: null pointer / bad argument";
+    return TDC_EINVAL;
+  }
+  const char* err = nullptr;
+  const int rc = window_rearrange_launch(in, in_dtype, bs, q, r, d, static_cast<__nv_bfloat16*>(out_bf16),
+                                         static_cast<cudaStream_t>(stream), &err);
+  if (rc != TDC_OK) g_create_error = err ? err : "tdc_window_rearrange failed";
+  return rc;
+}
+
+int tdc_combine_parts(const float* base, const float* parts, const float* logits, int32_t ld_logits, int32_t num_parts,
+                      int64_t rows, int32_t width, float* out, tdc_stream_t stream) {
+  if (rows == 0) return TDC_OK;
+  if (base == nullptr || parts == nullptr || logits == nullptr || out == nullptr || rows < 0) {
+    g_create_error = "tdc_combine_parts: null pointer / bad argument";
+    return TDC_EINVAL;
+  }
+  const char* err = nullptr;
+  const int rc = combine_parts_launch(base, parts, logits, ld_logits, num_parts, rows, width, out,
+                                      static_cast<cudaStream_t>(stream), &err);
+  if (rc != TDC_OK) g_create_error = err ? err : "tdc_combine_parts failed";
+  return rc;
+}
+
 int tdc_residual_add(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t count,
                      tdc_stream_t stream) {
   if (count == 0) return TDC_OK;

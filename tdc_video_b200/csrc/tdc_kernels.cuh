@@ -117,6 +117,12 @@ int assemble_static_launch(const __nv_bfloat16* xv, const __nv_bfloat16* xa, con
 // bilinear (align_corners = False) resize of a token grid, token-major: [bs, s_in^2, d] -> [bs, s_out^2, d]
 int resize_tokens_bilinear_launch(const void* in, int in_dtype, int bs, int s_in, int s_out, int d, void* out,
                                   int out_dtype, cudaStream_t stream, const char** err);
+// SVA connector: tokens under every query, window-major: in [bs, (q r)^2, d] -> out [bs, q, q, r, r, d] bf16
+int window_rearrange_launch(const void* in, int in_dtype, int bs, int q, int r, int d, __nv_bfloat16* out,
+                            cudaStream_t stream, const char** err);
+// out = base + sum_t softmax(logits[:, :T])[t] * parts[t]   (fp32 [rows, width]; parts [T, rows, width])
+int combine_parts_launch(const float* base, const float* parts, const float* logits, int ld_logits, int num_parts,
+                         long long rows, int width, float* out, cudaStream_t stream, const char** err);
 // out[i] = a[clamp(b[i], 0, n_a - 1)]
 int compose_index_launch(const int32_t* a, int n_a, const int32_t* b, int32_t* out, long long n, cudaStream_t stream,
                          const char** err);

@@ -171,6 +171,53 @@ def make_sva_state_dict(hidden: int, tower_dims, window_sides, num_layers: int, 
     return sd
 
 
+def make_sva_sep_state_dict(hidden: int, tower_dims, window_sides, num_layers: int, seed: int,
+                            stress: float = 1.0) -> Dict[str, np.ndarray]:
+    """As make_sva_state_dict, with `vision_sampler_0` made of VisionAggregationLayers (layer_type "sep",
+    tdc/vision_sampler.py:404-455): per tower an AggregationBlock (`aggregate_{t}.attention_layer.*`) and a
+    `weight_mlp` mixing the towers."""
+    rs = np.random.RandomState(seed)
+    sd: Dict[str, np.ndarray] = {}
+    f32 = np.float32
+
+    def lin(name, out_f, in_f, bias=False, scale=None):
+        sd[name + ".weight"] = (rs.standard_normal((out_f, in_f)) * (scale or 1.0 / np.sqrt(in_f))).astype(f32)
+        if bias:
+            sd[name + ".bias"] = (rs.standard_normal((out_f,)) * 0.05).astype(f32)
+
+    def ln(name, n):
+        sd[name + ".weight"] = (1.0 + 0.1 * rs.standard_normal((n,))).astype(f32)
+        sd[name + ".bias"] = (0.1 * rs.standard_normal((n,))).astype(f32)
+
+    for t, c in enumerate(tower_dims):
+        lin(f"mm_projector_aux_{t}.0", hidden, c, bias=True)
+        lin(f"mm_projector_aux_{t}.2", hidden, hidden, bias=True)
+        ln(f"mm_projector_aux_{t}.3", hidden)
+    sd["vision_query"] = rs.standard_normal((1, hidden)).astype(f32)
+    for i in range(num_layers):
+        p = f"vision_sampler_0.layers.{i}."
+        lin(p + "proj_context", hidden, hidden)
+        lin(p + "proj_in", hidden, 2 * hidden)
+        lin(p + "proj_out.linear_1", hidden, hidden)
+        lin(p + "proj_out.linear_2", hidden, hidden)
+        ln(p + "norm", hidden)
+        if len(window_sides) > 1:
+            lin(p + "weight_mlp.linear_1", hidden, 2 * hidden)
+            lin(p + "weight_mlp.linear_2", len(window_sides), hidden, scale=2.0 / np.sqrt(hidden))
+        for t, side in enumerate(window_sides):
+            a = p + f"aggregate_{t}.attention_layer."
+            if side > 1:
+                sd[p + f"pos_embed_{t}"] = rs.standard_normal((side * side, hidden)).astype(f32)
+                for nm in ("q_proj", "k_proj", "v_proj"):
+                    ln(a + nm + ".0", hidden)
+                    lin(a + nm + ".1", hidden, hidden, scale=(stress if nm != "v_proj" else 1.0) / np.sqrt(hidden))
+                lin(a + "o_proj", hidden, hidden)
+            else:
+                lin(a + "linear_1", hidden, hidden)
+                lin(a + "linear_2", hidden, hidden)
+    return sd
+
+
 def add_sva_group(sd: Dict[str, np.ndarray], group: int, hidden: int, window_sides, num_layers: int, seed: int,
                   stress: float = 1.0) -> None:
     """One more query group (`vision_query[group]`, `vision_sampler_{group}`; cambrian_arch.py:92-110, 139-142)."""

@@ -124,3 +124,21 @@ def test_resize_tokens_bilinear_matches_torch(s_in, s_out):
     ref = F.interpolate(x.permute(0, 2, 1).reshape(3, 64, s_in, s_in), size=(s_out, s_out), mode="bilinear",
                         align_corners=False).permute(0, 2, 3, 1).flatten(1, 2)
     assert torch.allclose(out, ref, atol=1e-5)
+
+
+@pytest.mark.parametrize("sides", [(2, 2), (2, 1)])
+def test_sva_sep_layers_vs_oracle(sides):
+    """layer_type "sep" (VisionAggregationLayer): per-tower attention / MLP, tdc_combine_parts for the softmax mix."""
+    from oracle.synth import make_sva_sep_state_dict
+    from tdc_video_b200.sva import SVAConnector
+    hidden, dims, layers, Q = 128, (96, 64), 2, 4
+    sizes = [(640, 360), (384, 384), (300, 500)]
+    sd = make_sva_sep_state_dict(hidden, dims, sides, layers, seed=11, stress=1.5)
+    tower = sva_inputs(dims, sides, Q, len(sizes), 9)
+    mod = SVAConnector(dims, sides, hidden=hidden, query_side=Q, num_layers=layers, layer_type="sep")
+    mod.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    mod = mod.cuda().eval()
+    out = mod([t.cuda() for t in tower], sizes)
+    torch.cuda.synchronize()
+    ref = sva_oracle.sva_frames(sd, tower, sizes, Q, layers, num_heads=hidden // 64, layer_type="sep")
+    _check(out, ref, f"sva sep sides{sides}")

@@ -121,3 +121,37 @@ def test_two_query_groups_equal_reference_modules():
     got = sva_oracle.sva_frames_groups(sd, tower, sizes, (final, coarse), final, layers)   # 16 heads, as the reference
     assert got.shape == ref.shape == (bs, final * final, 2 * hidden)
     assert float((got - ref).abs().max()) <= 5e-5
+
+
+@pytest.mark.parametrize("sides", [(2, 2), (2, 1)])
+def test_sep_layers_equal_reference_modules(sides):
+    """VisionTokenSampler(layer_type="sep") = VisionAggregationLayer (vision_sampler.py:404-517): per-tower attention
+    (an MLP where the window is a single token) mixed by softmax(weight_mlp): reference module vs the oracle."""
+    from oracle.synth import make_sva_sep_state_dict
+    vs = _load_vision_sampler()
+    hidden, dims, layers, Q = 128, (96, 64), 2, 4
+    sizes = [(640, 360), (384, 384), (300, 500)]
+    sd = make_sva_sep_state_dict(hidden, dims, sides, layers, seed=11, stress=2.0)
+    bs = len(sizes)
+    rs = np.random.RandomState(3)
+    tower = [torch.from_numpy(rs.standard_normal((bs, (Q * s) ** 2, c)).astype(np.float32)) for s, c in zip(sides, dims)]
+    sampler = vs.VisionTokenSampler(hidden, hidden, [hidden] * 2, list(sides), hidden, layers, "sep").eval()
+    sampler.load_state_dict({k[len("vision_sampler_0."):]: torch.from_numpy(v) for k, v in sd.items()
+                             if k.startswith("vision_sampler_0.")}, strict=True)
+    from oracle import harness
+    arch = harness._load_cambrian_arch()
+
+    class Bare(arch.CambrianMetaForCausalLM):
+        def get_model(self):
+            return None
+
+    with torch.no_grad():
+        feats = [sva_oracle.mm_projector_aux(sd, f"mm_projector_aux_{t}", tower[t]) for t in range(2)]
+        lat, masks = Bare().rearrange_vision_tower_features_inference(feats, Q, sizes)
+        nq = Q * Q
+        ctx = feats[0].mean(1).view(bs, 1, 1, -1).expand(-1, nq, 1, -1).flatten(0, 1)
+        qry = torch.from_numpy(sd["vision_query"])[0].view(1, 1, 1, -1).expand(bs, nq, -1, -1).flatten(0, 1)
+        ref = sampler(qry, ctx, *lat, *masks).view(bs, nq, hidden)
+    got = sva_oracle.sva_frames(sd, tower, sizes, Q, layers, layer_type="sep")
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 5e-5
