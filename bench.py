@@ -576,7 +576,9 @@ def bench_frames(args, w, ctx):
 
         S_s = S // world                        # this rank's contiguous range of video-seconds of THE video
         lo = rank * S_s
-        sb = [(lo + S_s * b // nb, lo + S_s * (b + 1) // nb) for b in range(nb)]
+        # ranges of <= 600 chunks (= one 1800-row internal batch of the library), at least `gather_batches` of them
+        nb_s = max(nb, -(-S_s // 600))
+        sb = [(lo + S_s * b // nb_s, lo + S_s * (b + 1) // nb_s) for b in range(nb_s)]
         mc_s, gath_s = None, None
         if mcast is not None:
             from tdc_video_b200.dist import MulticastGather
