@@ -532,8 +532,6 @@ def bench_frames(args, w, ctx):
         out = step()
     barrier()
     assert torch.isfinite(out[:8].float()).all()
-    eng.set_profiling(True)
-    eng.reset_profile()
     launches0 = eng.launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -548,10 +546,18 @@ def bench_frames(args, w, ctx):
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - launches0
+    # per-kernel-class device times come from a SEPARATE profiled pass (two CUDA events around every launch would
+    # otherwise sit inside the timed region: ~1800 event records per step)
+    psteps = max(1, min(args.steps, 5))
+    eng.set_profiling(True)
+    eng.reset_profile()
+    for _ in range(psteps):
+        step()
+    barrier()
     prof = eng.profile()
     eng.set_profiling(False)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    mine = torch.tensor([ms / args.steps, sum(v["ms"] for v in prof.values()) / args.steps], dtype=torch.float64, device=dev)
+    mine = torch.tensor([ms / args.steps, sum(v["ms"] for v in prof.values()) / psteps], dtype=torch.float64, device=dev)
     per_rank = [mine.clone() for _ in range(world)]
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -643,7 +649,7 @@ def bench_frames(args, w, ctx):
         exec_s = model_s
         kv_exec_s = (F_ - 1) * 2 * (144 + Ta) * d * 2 * H * N_CROSS
     kv_ms, kv_n = prof["kv_gemm"]["ms"], prof["kv_gemm"]["launches"]
-    kv_flops_total = kv_exec_s * S * args.steps
+    kv_flops_total = kv_exec_s * S * psteps
     kv_achieved = kv_flops_total / (kv_ms * 1e-3) / 1e12 if kv_ms > 0 else None
     line = {
         "metric": "video_seconds_per_sec", "value": value, "unit": "video-s/s", "n_gpus": world, "steps": args.steps,
@@ -664,23 +670,23 @@ def bench_frames(args, w, ctx):
                                "K=3584 + audio tokens K=768 per row batch)",
                      "bound": "tensor", "achieved": kv_achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": (kv_achieved / peaks["tflops_sustained"]) if kv_achieved else None,
-                     "traffic": (measured_traffic_per_row("kv_gemm_traffic_r02.json") * rows * args.steps / max(kv_n // 2, 1))
+                     "traffic": (measured_traffic_per_row("kv_gemm_traffic_r02.json") * rows * psteps / max(kv_n // 2, 1))
                      if (fold and measured_traffic_per_row("kv_gemm_traffic_r02.json")) else None,
                      "traffic_note": "DRAM read + write of ONE visual-token K/V launch = ncu bytes per row "
                                      "(profiles/kv_gemm_traffic_r02.json) x rows per launch; the audio-token launches "
                                      "(K = 768, ~8 % of the class time) are not in this figure; algorithmic = "
                                      "rows*144*(3584 + 9216)*2 B + the 66 MB weight",
-                     "algorithmic_bytes": rows * args.steps / max(kv_n // 2, 1) * 144 * (d + 2 * H * N_CROSS) * 2 + 2 * H * N_CROSS * d * 2,
+                     "algorithmic_bytes": rows * psteps / max(kv_n // 2, 1) * 144 * (d + 2 * H * N_CROSS) * 2 + 2 * H * N_CROSS * d * 2,
                      "flops": "EXECUTED by these launches (folded weights): rows x (2*144*3584 + 2*50*768) x 9216",
                      "peak_source": peaks["source"] + " bf16_tflops_sustained", "launches": kv_n,
-                     "avg_launch_ms": kv_ms / max(kv_n, 1), "share_of_step": kv_ms / (ms_step * args.steps)},
+                     "avg_launch_ms": kv_ms / max(kv_n, 1), "share_of_step": kv_ms / psteps / ms_step},
         "path": {"model_tflop_per_step": model_s * S / 1e12, "executed_tflop_per_step": exec_s * S / 1e12,
                  "model_tflops": model_s * S / (ms_step * 1e-3) / 1e12,
                  "executed_tflops": exec_s * S / (ms_step * 1e-3) / 1e12,
                  "executed_frac_of_sustained_peak": exec_s * S / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"],
                  "model_frac_of_sustained_peak": model_s * S / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"],
                  "gflop_per_video_second": {"model": model_s / 1e9, "executed": exec_s / 1e9},
-                 "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}},
+                 "kernel_ms_per_step": {k: v["ms"] / psteps for k, v in prof.items()}},
         "ranks": per_rank, "unfolded": unfolded,
     }
     if args.parity_rows > 0:
@@ -811,8 +817,6 @@ def bench_tokens(args, w, ctx):
         out = step()
     barrier()
     assert torch.isfinite(out[:8].float()).all()
-    eng.set_profiling(True)
-    eng.reset_profile()
     launches0 = eng.launch_count()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -827,11 +831,19 @@ def bench_tokens(args, w, ctx):
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - launches0   # our kernels only (NCCL's are not counted)
+    # per-kernel-class device times come from a SEPARATE profiled pass (two CUDA events around every launch would
+    # otherwise sit inside the timed region: ~1800 event records per step)
+    psteps = max(1, min(args.steps, 5))
+    eng.set_profiling(True)
+    eng.reset_profile()
+    for _ in range(psteps):
+        step()
+    barrier()
     prof = eng.profile()
     eng.set_profiling(False)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     # every rank's own device time and kernel-time sum (the step ends at a barrier, so `value` follows the slowest GPU)
-    mine = torch.tensor([ms / args.steps, sum(v["ms"] for v in prof.values()) / args.steps], dtype=torch.float64, device=dev)
+    mine = torch.tensor([ms / args.steps, sum(v["ms"] for v in prof.values()) / psteps], dtype=torch.float64, device=dev)
     per_rank = [mine.clone() for _ in range(world)]
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -953,7 +965,7 @@ def bench_tokens(args, w, ctx):
     peaks = measured_peaks()
     f_row, f_row_kv = flops_per_row(L, d_enc, K, T, d_out, w["projector"])
     kv_ms, kv_n = prof["kv_gemm"]["ms"], prof["kv_gemm"]["launches"]
-    kv_flops_per_launch = f_row_kv * rows * args.steps / max(kv_n, 1)
+    kv_flops_per_launch = f_row_kv * rows * psteps / max(kv_n, 1)
     kv_achieved = kv_flops_per_launch / (kv_ms / max(kv_n, 1) * 1e-3) / 1e12 if kv_ms > 0 else None
     path_tflops = f_row * rows / (ms_step * 1e-3) / 1e12
     line = {
@@ -973,16 +985,16 @@ def bench_tokens(args, w, ctx):
         "roofline": {"kernel": "tdc_gemm_kernel (cross-attn K/V projection, all 6 layers, N=9216)", "bound": "tensor",
                      "achieved": kv_achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": (kv_achieved / peaks["tflops_sustained"]) if kv_achieved else None,
-                     "traffic": (measured_traffic_per_row() * rows * args.steps / max(kv_n, 1))
+                     "traffic": (measured_traffic_per_row() * rows * psteps / max(kv_n, 1))
                      if measured_traffic_per_row() else None,
                      "traffic_note": "bytes per launch = ncu dram read+write per row (profiles/kv_gemm_traffic.json) x rows "
                                      "per launch; algorithmic = rows*L*(d_enc + 9216)*2 B",
-                     "algorithmic_bytes": rows * args.steps / max(kv_n, 1) * L * (d_enc + 2 * H * N_CROSS) * 2,
+                     "algorithmic_bytes": rows * psteps / max(kv_n, 1) * L * (d_enc + 2 * H * N_CROSS) * 2,
                      "peak_source": peaks["source"] + " bf16_tflops_sustained", "launches": kv_n,
-                     "avg_launch_ms": kv_ms / max(kv_n, 1), "share_of_step": kv_ms / (ms_step * args.steps)},
+                     "avg_launch_ms": kv_ms / max(kv_n, 1), "share_of_step": kv_ms / psteps / ms_step},
         "path": {"algorithmic_tflops": path_tflops, "frac_of_sustained_peak": path_tflops / peaks["tflops_sustained"],
                  "gflop_per_row": f_row / 1e9,
-                 "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()}},
+                 "kernel_ms_per_step": {k: v["ms"] / psteps for k, v in prof.items()}},
         "ranks": per_rank,
     }
     if args.parity_rows > 0 and mlp is None:

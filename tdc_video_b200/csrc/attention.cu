@@ -63,6 +63,8 @@ struct KVRegs {
 // self-attention) so the per-token slab-row lookup collapses to base + token.
 template <bool kTwoSeg>
 __global__ void __launch_bounds__(128, 4) tdc_attention_kernel(AttentionArgs a) {
+  grid_dependency_wait();
+  grid_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2;  // MMA "group" id: fragment row / column owner
   const int c = lane & 3;   // thread within group
@@ -293,11 +295,19 @@ int attention_launch(const AttentionArgs& a, cudaStream_t stream, const char** e
       attr_set[dev] = true;
     }
   }
-  if (a.q_seg2 > 0 || a.kv_seg2 > 0 || a.kv_seg3 > 0)
-    tdc_attention_kernel<true><<<static_cast<unsigned>(blocks), 128, kSmem, stream>>>(a);
-  else
-    tdc_attention_kernel<false><<<static_cast<unsigned>(blocks), 128, kSmem, stream>>>(a);
-  const cudaError_t rc = cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(blocks));
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = kSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  const bool segs = a.q_seg2 > 0 || a.kv_seg2 > 0 || a.kv_seg3 > 0;
+  const cudaError_t rc = segs ? cudaLaunchKernelEx(&cfg, tdc_attention_kernel<true>, a)
+                              : cudaLaunchKernelEx(&cfg, tdc_attention_kernel<false>, a);
   if (rc != cudaSuccess) {
     if (err) *err = cudaGetErrorString(rc);
     return TDC_ECUDA;

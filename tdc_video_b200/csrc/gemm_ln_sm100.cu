@@ -171,6 +171,9 @@ tdc_gemm_ln_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   cluster_sync_all();  // every CTA's stats barriers exist before any peer's st.async can land
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_base_smem;
+  // everything above (barriers, TMEM, descriptor prefetch) may overlap the previous kernel's tail
+  grid_dependency_wait();
+  grid_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs of the pair; bytes are credited to the leader's barrier) =====
@@ -550,11 +553,16 @@ int launch_ln(const GemmLnProblem& p, cudaStream_t stream, const char** err) {
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = L::kTotalBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (pdl_enabled()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   const cudaError_t rc = cudaLaunchKernelEx(&cfg, kernel, map_a, map_w, map_f32, map_bf16, p.m, p.n, p.k, cluster, ln);
   if (rc != cudaSuccess) {
     if (err) *err = cudaGetErrorString(rc);

@@ -5,6 +5,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda.h>
@@ -36,6 +37,18 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n"
                "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------
+// programmatic dependent launch (the kernel may start while its predecessor in the stream drains; it must not touch
+// the predecessor's data before grid_dependency_wait() returns).  No-ops when launched without the attribute.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// host side: TDC_PDL=1 (dev knob, read once) adds cudaLaunchAttributeProgrammaticStreamSerialization to the launches
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("TDC_PDL"); return e != nullptr && atoi(e) == 1; }();
+  return on;
 }
 
 // ----------------------------------------------------------------------------
