@@ -23,6 +23,7 @@ def main():
     comp = TDCCompressor(d, context_token_num=16, query_type="Avg_pool", text_input=True, add_static=True,
                          audio_input=True).to(dev).eval()
     g = torch.Generator(device=dev).manual_seed(5)
+    g0 = torch.Generator(device=dev).manual_seed(6)
     frames = torch.randn(n, 156, d, device=dev, generator=g).to(torch.bfloat16)
     # DINO features: slow drift + a jump every ~9 frames so that the 24 boundaries are well defined
     drift = torch.cumsum(torch.randn(n, 1, 1536, device=dev, generator=g) * 0.05, 0)
@@ -85,13 +86,40 @@ def main():
     graph_dev, graph_wall = timed(g.replay)
     engine = {"rows": int(R), "eager_ms": eager_dev, "eager_wall_ms": eager_wall, "graph_ms": graph_dev,
               "graph_wall_ms": graph_wall}
+
+    # the same video from the TOWERS' outputs (round 2): mm_projector + newline + audio_proj + queries + Q-Former in one
+    # tdc_compress_frames call (weights folded), adapt_segment and audio pooling as above
+    comp2 = TDCCompressor(d, context_token_num=16, query_type="Avg_pool", text_input=True, add_static=True,
+                          audio_input=True, mm_input_size=1024).to(dev).eval()
+    feats = torch.randn(n, 144, 1024, device=dev, generator=g0).to(torch.bfloat16)
+
+    def run2():
+        return tdc_video_stage(comp2, None, dino, tower_features=feats, **kw)
+
+    for _ in range(3):
+        out2 = run2()
+    torch.cuda.synchronize()
+    walls2, devs2 = [], []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record()
+        out2 = run2()
+        e1.record()
+        torch.cuda.synchronize()
+        walls2.append((time.perf_counter() - t0) * 1e3)
+        devs2.append(e0.elapsed_time(e1))
+    from_towers = {"wall_ms_median": float(np.median(walls2)), "device_ms_median": float(np.median(devs2)),
+                   "output_tokens": int(out2.shape[0]), "finite": bool(torch.isfinite(out2.float()).all()),
+                   "includes": "mm_projector on 224 frames (1.07 TFLOP), newline, audio_proj, query build"}
     print(json.dumps({
         "metric": "TDC stage latency, one 224-frame video (Qwen2-7B widths, L=206, K=16, T=32, audio)",
         "wall_ms_median": float(np.median(walls)), "wall_ms_min": float(min(walls)),
         "device_ms_median": float(np.median(devs)), "output_tokens": int(out.shape[0]),
         "rows": int(plan.num_rows), "chunks": int(plan.num_chunks),
         "reference_launch_pattern": f"{plan.num_chunks} Q-Former calls of <= 7 rows (cambrian_arch.py:1603-1692)",
-        "tdc_compress_alone": engine, "finite": bool(torch.isfinite(out.float()).all())}))
+        "tdc_compress_alone": engine, "from_towers": from_towers, "finite": bool(torch.isfinite(out.float()).all())}))
 
 
 if __name__ == "__main__":
