@@ -591,14 +591,71 @@ def bench_frames(args, w, ctx):
             mc_s = MulticastGather(S_s * (F_ - 1), (K, d), torch.bfloat16, dev)
         else:
             gath_s = torch.empty((world, S_s * (F_ - 1), K, d), dtype=torch.bfloat16, device=dev)
-        strong_step = make_step(sb, [plan_range(c0, c1) for c0, c1 in sb], mc_s, gath_s, lo, fold)
+        strong_plans = [plan_range(c0, c1) for c0, c1 in sb]
+        strong_step = make_step(sb, strong_plans, mc_s, gath_s, lo, fold)
         strong_ms = timed(strong_step, args.strong_steps)
         n1_ms = timed(lambda: compute_range(full_plan, 0, S, fold), max(2, args.strong_steps // 2))
         mine_s = compute_range(plan_range(lo, lo + S_s), lo, lo + S_s, fold, want_static=False)
         got = strong_step().reshape(world, S_s * (F_ - 1), K, d)[rank]
         flag = torch.tensor([int(torch.equal(got, mine_s))], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        # the same step when the key frames' pass-through tokens (produced sharded by the upstream entry: each rank
+        # projects its own key frames) are ALSO assembled on every rank: one NCCL all-gather per chunk range, issued
+        # right after the range's kernels so that it overlaps the next range's compute
+        Ls = 144 + 12 + Ta
+        key_bytes = S * Ls * d * 2
+        key_all = [torch.empty((world, c1 - c0, Ls, d), dtype=torch.bfloat16, device=dev) for c0, c1 in sb]
+
+        def strong_step_with_keys():
+            works = []
+            for i, ((c0, c1), pl) in enumerate(zip(sb, strong_plans)):
+                compute_range(pl, c0, c1, fold, mc_ptr=None if mc_s is None else mc_s.slot_ptr((c0 - lo) * (F_ - 1)))
+                works.append(dist.all_gather_into_tensor(key_all[i].view(world * (c1 - c0), Ls, d), static_out[c0:c1],
+                                                         async_op=True))
+            if mc_s is not None:
+                mc_s.barrier()
+            for wk in works:
+                wk.wait()
+
+        strong_keys_ms = timed(strong_step_with_keys, args.strong_steps) if mc_s is not None else None
+        del key_all
+        # ... and with the key frames' tokens stored through a second multicast mapping by the kernel that assembles
+        # them (tdc_frames_args.static_multicast): no collective at all, one device barrier closes both exchanges
+        strong_keys_mc_ms, keys_match = None, None
+        if mc_s is not None:
+            mc_k = MulticastGather(S_s, (Ls, d), torch.bfloat16, dev)
+
+            def strong_step_keys_multicast():
+                for (c0, c1), (st, rf, rc) in zip(sb, strong_plans):
+                    eng.compress_frames(frames_dev, st, rf, rc, audio=audio_dev, input_ids=ids_dev, num_query=K,
+                                        fold=fold, out_dtype=torch.bfloat16,
+                                        multicast_ptr=mc_s.slot_ptr((c0 - lo) * (F_ - 1)),
+                                        static_multicast_ptr=mc_k.slot_ptr(c0 - lo))
+                mc_s.barrier()
+                mc_k.barrier()
+
+            strong_keys_mc_ms = timed(strong_step_keys_multicast, args.strong_steps)
+            # the multicast buffer must equal an NCCL all-gather of every rank's own key-frame tokens
+            compute_range(plan_range(lo, lo + S_s), lo, lo + S_s, fold)
+            ref_keys = torch.empty((world * S_s, Ls, d), dtype=torch.bfloat16, device=dev)
+            dist.all_gather_into_tensor(ref_keys, static_out[lo:lo + S_s].contiguous())
+            strong_step_keys_multicast()
+            barrier()
+            kflag = torch.tensor([int(torch.equal(mc_k.gathered, ref_keys))], device=dev)
+            dist.all_reduce(kflag, op=dist.ReduceOp.MIN)
+            keys_match = bool(kflag.item())
+            del ref_keys, mc_k
         strong = {"segments_total": S, "segments_per_gpu": S_s, "rows_per_gpu": S_s * (F_ - 1), "ms_per_step": strong_ms,
+                  "with_key_frames": None if strong_keys_ms is None else {
+                      "ms_per_step": strong_keys_mc_ms, "speedup_vs_n1": n1_ms / strong_keys_mc_ms,
+                      "gathered_bytes": key_bytes, "exchange_check": keys_match,
+                      "nccl_all_gather_ms_per_step": strong_keys_ms,
+                      "desc": "every rank also ends with ALL key frames' pass-through tokens [S, 206, d]: the kernel that "
+                              "assembles them stores through a second NVSwitch multicast mapping (multimem.st), so the "
+                              "complete ordered sequence of the video is on every GPU when the barrier returns; "
+                              "nccl_all_gather_ms_per_step = the same with one NCCL all-gather per chunk range instead. "
+                              "The synthetic unit has one key frame per second (4-frame chunks); the reference's 8-frame "
+                              "chunks halve this payload"},
                   "value": S / (strong_ms * 1e-3), "unit": "video-s/s", "one_gpu_ms_per_step": n1_ms,
                   "speedup_vs_n1": n1_ms / strong_ms, "steps": args.strong_steps, "exchange": exchange,
                   "own_rows_match": bool(flag.item()),

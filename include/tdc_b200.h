@@ -186,7 +186,8 @@ typedef struct tdc_frames_args {
   int32_t n_prompts;             /* rows of input_ids (0 or 1: a single prompt).  All index arrays are DEVICE data the
                                   * library cannot validate on the host: frame / chunk / prompt indices are clamped into
                                   * range on the device instead of being trusted */
-  int32_t reserved0;
+  int32_t static_multicast;      /* 1: `static_out` is an NVSwitch multicast address: the key frames' pass-through tokens are
+                                  * delivered to every GPU of the group by the kernel that assembles them */
 } tdc_frames_args;
 
 /* Workspace for tdc_compress_frames processing `batch` rows (and key frames) at a time; any size from

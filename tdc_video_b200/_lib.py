@@ -53,7 +53,7 @@ class TdcFramesArgs(C.Structure):
         ("learned_queries", C.c_int32), ("fold", C.c_int32), ("multicast", C.c_int32), ("out_dtype", C.c_int32),
         ("no_layer0_dedup", C.c_int32),
         ("static_out", C.c_void_p), ("out", C.c_void_p), ("chunk_prompt", C.c_void_p),
-        ("n_prompts", C.c_int32), ("reserved0", C.c_int32),
+        ("n_prompts", C.c_int32), ("static_multicast", C.c_int32),
     ]
 
 

@@ -104,7 +104,21 @@ __global__ void __launch_bounds__(256) pool_static_queries_kernel(const __nv_bfl
   }
 }
 
-// static_out[c] = [ (side visual tokens, newline) x side | Ta audio tokens ]  in out_dtype (bf16 / fp16 / fp32)
+// 16-byte store; kMulticast: `p` is an NVSwitch multicast address (multimem.st: every GPU of the group gets the bytes)
+template <bool kMulticast>
+__device__ __forceinline__ void store16_mc(void* p, uint4 v) {
+  if (kMulticast)
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+  else
+    *reinterpret_cast<uint4*>(p) = v;
+}
+
+// static_out[c] = [ (side visual tokens, newline) x side | Ta audio tokens ]  in out_dtype (bf16 / fp16 / fp32).
+// One warp per token, 16-byte stores; kMulticast: stored through an NVSwitch multicast address, so the key frames'
+// pass-through tokens land on every GPU of the group while the kernel runs (the all-gather fused into the producer).
+template <bool kMulticast>
 __global__ void __launch_bounds__(256) assemble_static_kernel(const __nv_bfloat16* __restrict__ xv,
                                                               const __nv_bfloat16* __restrict__ xa,
                                                               const float* __restrict__ newline, int chunks, int side,
@@ -124,29 +138,38 @@ __global__ void __launch_bounds__(256) assemble_static_kernel(const __nv_bfloat1
   }
   const size_t esz = out_dtype == TDC_F32 ? 4 : 2;
   uint8_t* dst = static_cast<uint8_t*>(out) + static_cast<size_t>(tok) * d * esz;
-  for (int j = lane; j < d / 4; j += 32) {
-    float4 v;
+  for (int j = lane; j < d / 8; j += 32) {   // 8 columns per lane and iteration
+    float v[8];
     if (src != nullptr) {
-      const uint2 raw = __ldg(reinterpret_cast<const uint2*>(src) + j);
-      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
-      const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-      v = make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src) + j);
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 p2 = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+        v[2 * e] = __low2float(p2);
+        v[2 * e + 1] = __high2float(p2);
+      }
     } else {
-      v = __ldg(reinterpret_cast<const float4*>(newline) + j);
+      const float4 a = __ldg(reinterpret_cast<const float4*>(newline) + 2 * j);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(newline) + 2 * j + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     }
     if (out_dtype == TDC_F32) {
-      reinterpret_cast<float4*>(dst)[j] = v;
+      store16_mc<kMulticast>(dst + j * 32, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
+                                                      __float_as_uint(v[3])));
+      store16_mc<kMulticast>(dst + j * 32 + 16, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]),
+                                                           __float_as_uint(v[6]), __float_as_uint(v[7])));
     } else if (out_dtype == TDC_BF16) {
-      uint2 pk;
-      pk.x = pack_bf16x2(v.x, v.y);
-      pk.y = pack_bf16x2(v.z, v.w);
-      reinterpret_cast<uint2*>(dst)[j] = pk;
+      store16_mc<kMulticast>(dst + j * 16, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                      pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
     } else {
-      const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-      uint2 pk;
-      pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-      pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-      reinterpret_cast<uint2*>(dst)[j] = pk;
+      uint32_t h[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      }
+      store16_mc<kMulticast>(dst + j * 16, make_uint4(h[0], h[1], h[2], h[3]));
     }
   }
 }
@@ -343,15 +366,19 @@ int pool_static_queries_launch(const __nv_bfloat16* xv, const float* newline, in
 }
 
 int assemble_static_launch(const __nv_bfloat16* xv, const __nv_bfloat16* xa, const float* newline, int chunks, int side,
-                           int ta, int d, void* out, int out_dtype, cudaStream_t stream, const char** err) {
+                           int ta, int d, void* out, int out_dtype, bool multicast, cudaStream_t stream,
+                           const char** err) {
   if (chunks <= 0) return TDC_OK;
   const long long toks = static_cast<long long>(chunks) * (side * (side + 1) + ta);
-  if (d % 4 != 0) {
-    if (err) *err = "assemble_static: d must be a multiple of 4";
+  if (d % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 15)) {
+    if (err) *err = "assemble_static: d must be a multiple of 8 and the output 16-byte aligned";
     return TDC_EINVAL;
   }
-  assemble_static_kernel<<<static_cast<unsigned>((toks + 7) / 8), 256, 0, stream>>>(xv, xa, newline, chunks, side, ta, d,
-                                                                                    out, out_dtype);
+  const unsigned blocks = static_cast<unsigned>((toks + 7) / 8);
+  if (multicast)
+    assemble_static_kernel<true><<<blocks, 256, 0, stream>>>(xv, xa, newline, chunks, side, ta, d, out, out_dtype);
+  else
+    assemble_static_kernel<false><<<blocks, 256, 0, stream>>>(xv, xa, newline, chunks, side, ta, d, out, out_dtype);
   return launched(err);
 }
 

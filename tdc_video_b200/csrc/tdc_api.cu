@@ -689,7 +689,7 @@ int frames_static_batch(tdc_handle* h, const FramesCall& fc, const FramesWorkspa
     KernelScope ks(h, TDC_K_FRONTEND, s);
     TDC_TRY(assemble_static_launch(w.xv, w.xa, h->newline, static_cast<int>(cb), fc.side, Ta, D,
                                    static_cast<uint8_t*>(a.static_out) + static_cast<size_t>(c0) * ls * D * osz,
-                                   a.out_dtype, s, &err));
+                                   a.out_dtype, a.static_multicast != 0, s, &err));
   }
   return TDC_OK;
 }

@@ -112,8 +112,10 @@ int matvec_bias_launch(const __nv_bfloat16* w, const float* x, const float* b, f
 int pool_static_queries_launch(const __nv_bfloat16* xv, const float* newline, int chunks, int side, int d,
                                int num_query, __nv_bfloat16* out, cudaStream_t stream, const char** err);
 // static_out[c] = [(side visual tokens, newline) x side | ta audio tokens] (the key frame as it passes through)
+// (multicast: `out` is an NVSwitch multicast address, see l2_normalize_launch)
 int assemble_static_launch(const __nv_bfloat16* xv, const __nv_bfloat16* xa, const float* newline, int chunks, int side,
-                           int ta, int d, void* out, int out_dtype, cudaStream_t stream, const char** err);
+                           int ta, int d, void* out, int out_dtype, bool multicast, cudaStream_t stream,
+                           const char** err);
 // bilinear (align_corners = False) resize of a token grid, token-major: [bs, s_in^2, d] -> [bs, s_out^2, d]
 int resize_tokens_bilinear_launch(const void* in, int in_dtype, int bs, int s_in, int s_out, int d, void* out,
                                   int out_dtype, cudaStream_t stream, const char** err);

@@ -286,7 +286,7 @@ class QFormerEngine:
                         input_ids: Optional[torch.Tensor] = None, num_query: int = 16, learned_queries: bool = False,
                         fold: bool = True, want_static: bool = True, out_dtype=torch.bfloat16,
                         multicast_ptr: Optional[int] = None, layer0_dedup: bool = True,
-                        chunk_prompt: Optional[torch.Tensor] = None):
+                        chunk_prompt: Optional[torch.Tensor] = None, static_multicast_ptr: Optional[int] = None):
         """The TDC stage from the towers' outputs (tdc_compress_frames): mm_projector, image_newline, audio_proj,
         query build, Q-Former, vision_proj + L2-normalise for all chunks of a video in one call.
 
@@ -325,7 +325,12 @@ class QFormerEngine:
             raise ValueError("several prompts need chunk_prompt")
         side = int(round(Tv ** 0.5))
         d = self.cfg.d_out
-        static_out = torch.empty((C_, side * (side + 1) + Ta, d), dtype=out_dtype, device=dev) if want_static else None
+        static_out = None
+        if want_static and static_multicast_ptr is None:
+            static_out = torch.empty((C_, side * (side + 1) + Ta, d), dtype=out_dtype, device=dev)
+        static_ptr = None if static_out is None else static_out.data_ptr()
+        if static_multicast_ptr is not None:     # the key frames' tokens go to a caller-owned multicast mapping
+            static_ptr = int(static_multicast_ptr)
         out = None if multicast_ptr is not None else torch.empty((R, num_query, d), dtype=out_dtype, device=dev)
         if C_ == 0 and R == 0:
             return static_out, out
@@ -333,9 +338,10 @@ class QFormerEngine:
         a = TdcFramesArgs(frames.data_ptr(), None if audio is None else audio.data_ptr(), sf.data_ptr(), rf.data_ptr(),
                           rc_.data_ptr(), None if ids is None else ids.data_ptr(), n_frames, C_, R, Tv, Ta, num_query,
                           T, int(learned_queries), int(fold), int(multicast_ptr is not None), _DTYPES[out_dtype],
-                          int(not layer0_dedup), None if static_out is None else static_out.data_ptr(),
+                          int(not layer0_dedup), static_ptr,
                           int(multicast_ptr) if multicast_ptr is not None else out.data_ptr(),
-                          None if cp is None else cp.data_ptr(), 0 if ids is None else int(ids.shape[0]), 0)
+                          None if cp is None else cp.data_ptr(), 0 if ids is None else int(ids.shape[0]),
+                          int(static_multicast_ptr is not None))
         with torch.cuda.device(dev):
             rc = self.lib.tdc_compress_frames(self._h, C.byref(a), _ptr(ws), ws.numel(), _stream(dev))
         check(rc, self._h, "tdc_compress_frames")
