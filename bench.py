@@ -50,6 +50,12 @@ WORKLOADS = {
     # 3 rows per segment; row KV = 144 visual + 12 newline + 50 audio tokens.
     "hour_qwen7b": dict(segments=3600, frames_per_segment=4, kv_tokens=206, audio_tokens=50, d_enc=3584, d_out=3584,
                         num_query=16, num_text=0, label="1-hour video, Qwen2-7B widths (d=3584), L=206, K=16"),
+    # SURVEY.md 8d config 3, reference-faithful variant: the same hour sampled at 1 fps (3600 frames), chunks of 8 frames
+    # (cambrian_arch.py:1603-1628: <= 8 frames per Q-Former call, the first one the key frame) -> 450 chunks x 7 rows
+    "hour_1fps_chunk8": dict(segments=450, frames_per_segment=8, video_seconds_per_segment=8, kv_tokens=206,
+                             audio_tokens=50, d_enc=3584, d_out=3584, num_query=16, num_text=0,
+                             label="1-hour video at 1 fps in 8-frame chunks (450 chunks x 7 rows), Qwen2-7B widths, "
+                                   "L=206, K=16"),
     # BASELINE.json config 2: 256 segments, Llama-3.2-3B widths
     "cfg2_llama3b": dict(segments=256, frames_per_segment=4, kv_tokens=206, audio_tokens=50, d_enc=3072, d_out=3072,
                          num_query=16, num_text=0, label="256-segment video, Llama-3.2-3B widths (d=3072), L=206, K=16"),
@@ -83,8 +89,13 @@ def flops_per_row(L, d_enc, K, T, d_out, projector="vision_proj"):
     return kv + rest, kv
 
 
+def vsec(w):
+    """video-seconds one segment (= chunk) stands for"""
+    return w.get("video_seconds_per_segment", 1)
+
+
 def frames_flops(w, tv=144, d_in=1024, d_audio=768):
-    """Per video-second of the frames entry: (model FLOPs in the reference formulation, executed FLOPs with the
+    """Per SEGMENT (= one video-second in the canonical unit) of the frames entry: (model FLOPs in the reference formulation, executed FLOPs with the
     folded weights, executed FLOPs of the K/V projection GEMMs alone)."""
     F_, L, d, K, T = w["frames_per_segment"], w["kv_tokens"], w["d_enc"], w["num_query"], w.get("num_text", 0)
     ta = w["audio_tokens"]
@@ -230,7 +241,7 @@ def cpu_baseline_frames(geom, sd, w, sample_rows, seed, passes=1):
         for _ in range(passes):
             frames_oracle.frames_stage(sd_t, geom, frames, audio, cs, cl, w["num_query"], ids)
         dt = time.perf_counter() - t0
-    return passes * segs / dt, dt, cores
+    return passes * segs * vsec(w) / dt, dt, cores
 
 
 def cpu_baseline(geom, sd, w, sample_rows, seed, passes=1):
@@ -265,7 +276,7 @@ def cpu_baseline_tokens(geom, sd, w, sample_rows, seed, passes=1):
             run(inp["query_embeds"], inp["enc"], ids)
         dt = time.perf_counter() - t0
     rows_per_s = passes * sample_rows / dt
-    return rows_per_s / (w["frames_per_segment"] - 1), dt, cores
+    return rows_per_s / (w["frames_per_segment"] - 1) * vsec(w), dt, cores
 
 
 def cpu_baseline_reference_batching(geom, sd, w, sample_rows, seed):
@@ -283,7 +294,7 @@ def cpu_baseline_reference_batching(geom, sd, w, sample_rows, seed):
             sl = slice(r0, min(r0 + 7, sample_rows))
             oracle.compress(sd_t, geom, inp["query_embeds"][sl], inp["enc"][sl], None if ids is None else ids[sl])
         dt = time.perf_counter() - t0
-    return sample_rows / dt / (w["frames_per_segment"] - 1)
+    return sample_rows / dt / (w["frames_per_segment"] - 1) * vsec(w)
 
 
 def run_reference_arm(args, w):
@@ -307,7 +318,7 @@ def run_reference_arm(args, w):
                    "entry": "frames (oracle/frames_oracle.py: mm_projector, newline, audio_proj, query build, Q-Former, "
                             "vision_proj)" if w.get("entry") == "frames" else "tokens (oracle/qformer_oracle.py)"},
         "cpu_baseline": {"value": value, "unit": "video-s/s", "cores": cores, "kind": "port",
-                         "sample": f"{passes} x {sample} rows (= {passes * sample / (w['frames_per_segment'] - 1):.1f} "
+                         "sample": f"{passes} x {sample} rows (= {passes * sample / (w['frames_per_segment'] - 1) * vsec(w):.1f} "
                                    f"video-s) of the workload per step, oracle port of the reference (fp32 torch, "
                                    f"{sample}-row batches)"},
         "e2e": {"value": value, "unit": "video-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -565,7 +576,7 @@ def bench_frames(args, w, ctx):
     per_rank = {"ms_per_step": [round(float(x[0]), 2) for x in per_rank],
                 "kernel_ms_per_step": [round(float(x[1]), 2) for x in per_rank]}
     ms_step = float(t.item()) / args.steps
-    value = world * S / (ms_step * 1e-3)
+    value = world * S * vsec(w) / (ms_step * 1e-3)
 
     # ---- N > 1: the exchange verifies itself, then ONE video sharded over the N GPUs (strong scaling)
     exchange_check, strong = None, None
@@ -656,7 +667,7 @@ def bench_frames(args, w, ctx):
                               "nccl_all_gather_ms_per_step = the same with one NCCL all-gather per chunk range instead. "
                               "The synthetic unit has one key frame per second (4-frame chunks); the reference's 8-frame "
                               "chunks halve this payload"},
-                  "value": S / (strong_ms * 1e-3), "unit": "video-s/s", "one_gpu_ms_per_step": n1_ms,
+                  "value": S * vsec(w) / (strong_ms * 1e-3), "unit": "video-s/s", "one_gpu_ms_per_step": n1_ms,
                   "speedup_vs_n1": n1_ms / strong_ms, "steps": args.strong_steps, "exchange": exchange,
                   "own_rows_match": bool(flag.item()),
                   "limiter": "per-GPU step = compute of S/N segments + the device barrier that closes the multicast "
@@ -667,7 +678,7 @@ def bench_frames(args, w, ctx):
     unfolded = None
     if world == 1 and args.unfolded_steps > 0 and fold:
         u_ms = timed(make_step(cb, plans, None, None, 0, False), args.unfolded_steps, warm=1)
-        unfolded = {"ms_per_step": u_ms, "value": S / (u_ms * 1e-3), "unit": "video-s/s", "steps": args.unfolded_steps,
+        unfolded = {"ms_per_step": u_ms, "value": S * vsec(w) / (u_ms * 1e-3), "unit": "video-s/s", "steps": args.unfolded_steps,
                     "desc": "fold = 0: mm_projector.2 and audio_proj run on every frame, K/V from the d_llm-wide tokens"}
 
     # ---- end to end: the towers' outputs in pinned host memory, compressed tokens back in host memory
@@ -675,7 +686,8 @@ def bench_frames(args, w, ctx):
     if not args.no_e2e:
         out_host = torch.empty((rows, K, d), dtype=torch.bfloat16, pin_memory=pinned)
         kw = dict(input_ids=None if ids_dev is None else ids_dev.cpu(), num_query=K, fold=fold, static_out=static_out,
-                  chunks_per_batch=args.e2e_chunks_per_batch, taper_head=not args.e2e_no_head_taper)
+                  chunks_per_batch=min(args.e2e_chunks_per_batch, max(1, S // 6)),
+                  taper_head=not args.e2e_no_head_taper)
         if world > 1:
             kw["out_device"] = torch.empty((rows, K, d), dtype=torch.bfloat16, device=dev)
             if gathered is None:
@@ -690,7 +702,7 @@ def bench_frames(args, w, ctx):
         same = bool(torch.equal(out_host[:64].to(dev), compute_range(plan_range(0, 64 // (F_ - 1) + 1), 0,
                                                                      64 // (F_ - 1) + 1, fold, want_static=False)[:64]))
         h2d = frames_host.numel() * 2 + (audio_host.numel() * 2 if Ta else 0) + S * 4 + 2 * rows * 4
-        e2e = {"value": world * S / (e2e_ms * 1e-3), "unit": "video-s/s", "ms_per_step": e2e_ms, "steps": args.e2e_steps,
+        e2e = {"value": world * S * vsec(w) / (e2e_ms * 1e-3), "unit": "video-s/s", "ms_per_step": e2e_ms, "steps": args.e2e_steps,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host.numel() * 2,
                "host_memory": "pinned" if pinned else "pageable", "matches_resident": same,
                "api": "QFormerEngine.compress_frames_host (tdc_compress_frames per range of chunks; H2D of the "
@@ -742,7 +754,7 @@ def bench_frames(args, w, ctx):
                  "executed_tflops": exec_s * S / (ms_step * 1e-3) / 1e12,
                  "executed_frac_of_sustained_peak": exec_s * S / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"],
                  "model_frac_of_sustained_peak": model_s * S / (ms_step * 1e-3) / 1e12 / peaks["tflops_sustained"],
-                 "gflop_per_video_second": {"model": model_s / 1e9, "executed": exec_s / 1e9},
+                 "gflop_per_video_second": {"model": model_s / vsec(w) / 1e9, "executed": exec_s / vsec(w) / 1e9},
                  "kernel_ms_per_step": {k: v["ms"] / psteps for k, v in prof.items()}},
         "ranks": per_rank, "unfolded": unfolded,
     }
@@ -764,7 +776,7 @@ def bench_frames(args, w, ctx):
         passes = args.cpu_passes or 12
         v, dt, cores = cpu_baseline(geom, sd, w, args.cpu_sample_rows, 99, passes)
         line["cpu_baseline"] = {"value": v, "unit": "video-s/s", "cores": cores, "kind": "port",
-                                "sample": f"{passes} x {args.cpu_sample_rows // (F_ - 1)} video-seconds of the same "
+                                "sample": f"{passes} x {args.cpu_sample_rows // (F_ - 1) * vsec(w)} video-seconds of the same "
                                           f"workload in {dt:.1f} s (oracle port of the reference from the towers' "
                                           f"outputs, fp32 torch, one batched call per pass)"}
     return line
@@ -908,7 +920,7 @@ def bench_tokens(args, w, ctx):
     per_rank = {"ms_per_step": [round(float(x[0]), 2) for x in per_rank],
                 "kernel_ms_per_step": [round(float(x[1]), 2) for x in per_rank]}
     ms_step = float(t.item()) / args.steps
-    value = world * S / (ms_step * 1e-3)
+    value = world * S * vsec(w) / (ms_step * 1e-3)
 
     # ---- the exchange verifies itself: every rank's locally computed rows, all-gathered by NCCL, must equal
     # bit for bit what the timed step left in the gather buffer on EVERY rank (multicast stores + device barrier,
@@ -980,7 +992,7 @@ def bench_tokens(args, w, ctx):
         flag = torch.tensor([int(torch.equal(got, mine_s))], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         strong = {"segments_total": S, "segments_per_gpu": S // world, "rows_per_gpu": rows_s, "ms_per_step": strong_ms,
-                  "value": S / (strong_ms * 1e-3), "unit": "video-s/s", "one_gpu_ms_per_step": n1_ms,
+                  "value": S * vsec(w) / (strong_ms * 1e-3), "unit": "video-s/s", "one_gpu_ms_per_step": n1_ms,
                   "speedup_vs_n1": n1_ms / strong_ms, "steps": args.strong_steps, "exchange": exchange,
                   "own_rows_match": bool(flag.item()),
                   "limiter": "per-GPU step = compute of S/N segments + device barrier closing the multicast exchange; "
@@ -1011,7 +1023,7 @@ def bench_tokens(args, w, ctx):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_ms = float(te.item()) / args.e2e_steps
-        e2e = {"value": world * S / (e2e_ms * 1e-3), "unit": "video-s/s", "ms_per_step": e2e_ms,
+        e2e = {"value": world * S * vsec(w) / (e2e_ms * 1e-3), "unit": "video-s/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": enc_host.numel() * 2 + q_sets.numel() * 4 + query_set.numel() * 4,
                "d2h_bytes_per_step": out_host.numel() * 2, "host_memory": "pinned" if pinned else "pageable",
                "api": "QFormerEngine.compress_host (tdc_compress per row batch, H2D / compute / D2H on 3 streams)"}

@@ -35,6 +35,15 @@ def test_variant_workloads_and_projector_flops():
     assert kv_a == kv_b and b - a == 2 * 16 * 3584 * 3584
 
 
+def test_one_fps_chunk8_workload_is_the_same_hour():
+    # SURVEY.md 8d config 3, reference-faithful variant: 3600 frames at 1 fps in chunks of 8 -> 3150 rows, and the
+    # metric's unit stays video-seconds (8 per chunk)
+    w = bench.WORKLOADS["hour_1fps_chunk8"]
+    assert w["segments"] * w["frames_per_segment"] == 3600
+    assert w["segments"] * (w["frames_per_segment"] - 1) == 3150
+    assert w["segments"] * bench.vsec(w) == 3600 and bench.vsec(bench.WORKLOADS["hour_qwen7b"]) == 1
+
+
 def test_default_workload_is_the_north_star_config():
     w = bench.WORKLOADS["hour_qwen7b"]
     assert w["segments"] == 3600 and w["d_enc"] == 3584 and w["d_out"] == 3584 and w["num_query"] == 16
