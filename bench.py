@@ -645,11 +645,36 @@ def bench_frames(args, w, ctx):
                 mc_s.barrier()
                 mc_k.barrier()
 
-            strong_keys_mc_ms = timed(strong_step_keys_multicast, args.strong_steps)
-            # the multicast buffer must equal an NCCL all-gather of every rank's own key-frame tokens
+            key_ready = [torch.cuda.Event() for _ in sb]
+
+            def strong_step_keys_overlapped(mode="dma"):
+                # the key frames' tokens are complete early in the call (static_ready_event): the copy engines (or a
+                # few CTAs) on side streams ship them to every rank while the range's rows are being compressed
+                for i, ((c0, c1), (st, rf, rc)) in enumerate(zip(sb, strong_plans)):
+                    so, _ = eng.compress_frames(frames_dev, st, rf, rc, audio=audio_dev, input_ids=ids_dev, num_query=K,
+                                                fold=fold, out_dtype=torch.bfloat16,
+                                                multicast_ptr=mc_s.slot_ptr((c0 - lo) * (F_ - 1)),
+                                                static_ready_event=key_ready[i])
+                    mc_k.put_async(so, c0 - lo, after=key_ready[i], mode=mode)
+                mc_k.barrier()
+                mc_s.barrier()
+
+            strong_keys_ov_ms = timed(strong_step_keys_overlapped, args.strong_steps)
+            strong_keys_mm_ms = timed(lambda: strong_step_keys_overlapped("multimem"), args.strong_steps)
             compute_range(plan_range(lo, lo + S_s), lo, lo + S_s, fold)
             ref_keys = torch.empty((world * S_s, Ls, d), dtype=torch.bfloat16, device=dev)
             dist.all_gather_into_tensor(ref_keys, static_out[lo:lo + S_s].contiguous())
+            mc_k.buf.zero_()
+            barrier()
+            strong_step_keys_overlapped()
+            barrier()
+            kflag = torch.tensor([int(torch.equal(mc_k.gathered, ref_keys))], device=dev)
+            dist.all_reduce(kflag, op=dist.ReduceOp.MIN)
+            keys_ov_match = bool(kflag.item())
+            mc_k.buf.zero_()
+            barrier()
+            strong_keys_mc_ms = timed(strong_step_keys_multicast, args.strong_steps)
+            # the multicast buffer must equal an NCCL all-gather of every rank's own key-frame tokens
             strong_step_keys_multicast()
             barrier()
             kflag = torch.tensor([int(torch.equal(mc_k.gathered, ref_keys))], device=dev)
@@ -658,15 +683,22 @@ def bench_frames(args, w, ctx):
             del ref_keys, mc_k
         strong = {"segments_total": S, "segments_per_gpu": S_s, "rows_per_gpu": S_s * (F_ - 1), "ms_per_step": strong_ms,
                   "with_key_frames": None if strong_keys_ms is None else {
-                      "ms_per_step": strong_keys_mc_ms, "speedup_vs_n1": n1_ms / strong_keys_mc_ms,
-                      "gathered_bytes": key_bytes, "exchange_check": keys_match,
+                      "ms_per_step": strong_keys_ov_ms, "speedup_vs_n1": n1_ms / strong_keys_ov_ms,
+                      "gathered_bytes": key_bytes, "exchange_check": bool(keys_ov_match and keys_match),
+                      "multimem_copy_side_stream_ms_per_step": strong_keys_mm_ms,
+                      "multicast_from_assemble_kernel_ms_per_step": strong_keys_mc_ms,
                       "nccl_all_gather_ms_per_step": strong_keys_ms,
-                      "desc": "every rank also ends with ALL key frames' pass-through tokens [S, 206, d]: the kernel that "
-                              "assembles them stores through a second NVSwitch multicast mapping (multimem.st), so the "
-                              "complete ordered sequence of the video is on every GPU when the barrier returns; "
-                              "nccl_all_gather_ms_per_step = the same with one NCCL all-gather per chunk range instead. "
-                              "The synthetic unit has one key frame per second (4-frame chunks); the reference's 8-frame "
-                              "chunks halve this payload"},
+                      "desc": "every rank also ends with ALL key frames' pass-through tokens [S, 206, d], i.e. the complete "
+                              "ordered sequence of the video.  ms_per_step: tdc_compress_frames records "
+                              "static_ready_event once the key frames of a range are assembled, and the copy engines "
+                              "write them into every peer's symmetric buffer on side streams (tdc_peer_copy; no SM taken "
+                              "from the persistent compute kernels) while the range's rows are compressed; "
+                              "multimem_copy_side_stream: the same with 16 CTAs storing through a second NVSwitch "
+                              "multicast mapping (tdc_multicast_copy) — they have to wait for an SM; "
+                              "multicast_from_assemble_kernel: the assembling kernel itself stores through the mapping "
+                              "(static_multicast = 1; its stores are fabric-bound and stall the compute stream); "
+                              "nccl_all_gather: one NCCL all-gather per chunk range instead.  The synthetic unit has one key "
+                              "frame per second (4-frame chunks); the reference's 8-frame chunks halve this payload"},
                   "value": S * vsec(w) / (strong_ms * 1e-3), "unit": "video-s/s", "one_gpu_ms_per_step": n1_ms,
                   "speedup_vs_n1": n1_ms / strong_ms, "steps": args.strong_steps, "exchange": exchange,
                   "own_rows_match": bool(flag.item()),

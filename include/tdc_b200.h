@@ -188,6 +188,9 @@ typedef struct tdc_frames_args {
                                   * range on the device instead of being trusted */
   int32_t static_multicast;      /* 1: `static_out` is an NVSwitch multicast address: the key frames' pass-through tokens are
                                   * delivered to every GPU of the group by the kernel that assembles them */
+  void* static_ready_event;      /* cudaEvent_t or NULL: recorded on `stream` as soon as `static_out` is complete (before the
+                                  * dynamic frames are processed), so that a caller can ship the key frames' tokens on another
+                                  * stream — e.g. tdc_multicast_copy — while the rows are being compressed */
 } tdc_frames_args;
 
 /* Workspace for tdc_compress_frames processing `batch` rows (and key frames) at a time; any size from
@@ -196,6 +199,19 @@ size_t tdc_frames_workspace_bytes(const tdc_handle* h, int32_t n_chunks, int32_t
                                   int32_t visual_tokens, int32_t audio_tokens, int32_t num_query, int32_t num_text);
 int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* workspace, size_t workspace_bytes,
                         tdc_stream_t stream);
+
+/* Copy `bytes` (a multiple of 16; both pointers 16-byte aligned) from local device memory to an NVSwitch multicast
+ * address with multimem.st: every GPU of the multicast group receives the bytes at the same offset of its buffer.
+ * `ctas` bounds the grid (0: 16) so that the copy can share the GPU with compute on another stream.  This is the
+ * exchange step of the sharded path (the key frames' tokens "ride the same all-gather") without a
+ * collective library call; the caller closes it with its group barrier.  No reference counterpart (the reference has no
+ * intra-video parallelism, eval/eval_mlvu.py:129-156). */
+int tdc_multicast_copy(const void* src, void* dst_multicast, size_t bytes, int32_t ctas, tdc_stream_t stream);
+
+/* Stream-ordered copy by the GPU's copy engines (cudaMemcpyAsync, device to device / peer): `dst` may be a peer GPU's
+ * mapping of a symmetric buffer.  The bulk variant of the exchange: it takes no SM from the persistent compute kernels
+ * that run beside it, where tdc_multicast_copy's CTAs would have to wait for one. */
+int tdc_peer_copy(const void* src, void* dst, size_t bytes, tdc_stream_t stream);
 
 /* ---- small dense helpers on the same path ---------------------------------------- */
 /* replaces: nn.Linear forward — query_proj / audio_proj / vision_proj as plain callables

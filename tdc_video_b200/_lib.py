@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "tdc_abi_version", "tdc_create", "tdc_destroy", "tdc_last_error", "tdc_load_weights", "tdc_workspace_bytes",
     "tdc_qformer_forward", "tdc_proj_norm", "tdc_compress", "tdc_compress_multicast", "tdc_frames_workspace_bytes",
     "tdc_compress_frames", "tdc_linear", "tdc_linear_layernorm", "tdc_gelu_mlp", "tdc_avg_pool_tokens",
-    "tdc_convert", "tdc_layernorm", "tdc_attention", "tdc_residual_add", "tdc_resize_tokens_bilinear", "tdc_window_rearrange", "tdc_combine_parts", "tdc_segment_workspace_bytes", "tdc_segment_boundaries", "tdc_set_profiling", "tdc_get_profile", "tdc_reset_profile", "tdc_launch_count",
+    "tdc_convert", "tdc_layernorm", "tdc_attention", "tdc_residual_add", "tdc_resize_tokens_bilinear", "tdc_window_rearrange", "tdc_combine_parts", "tdc_multicast_copy", "tdc_peer_copy", "tdc_segment_workspace_bytes", "tdc_segment_boundaries", "tdc_set_profiling", "tdc_get_profile", "tdc_reset_profile", "tdc_launch_count",
 ]
 
 
@@ -53,7 +53,7 @@ class TdcFramesArgs(C.Structure):
         ("learned_queries", C.c_int32), ("fold", C.c_int32), ("multicast", C.c_int32), ("out_dtype", C.c_int32),
         ("no_layer0_dedup", C.c_int32),
         ("static_out", C.c_void_p), ("out", C.c_void_p), ("chunk_prompt", C.c_void_p),
-        ("n_prompts", C.c_int32), ("static_multicast", C.c_int32),
+        ("n_prompts", C.c_int32), ("static_multicast", C.c_int32), ("static_ready_event", C.c_void_p),
     ]
 
 
@@ -96,6 +96,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.tdc_window_rearrange.restype = C.c_int
     lib.tdc_combine_parts.argtypes = [vp, vp, vp, i32, i32, i64, i32, vp, vp]
     lib.tdc_combine_parts.restype = C.c_int
+    lib.tdc_multicast_copy.argtypes = [vp, vp, C.c_size_t, i32, vp]
+    lib.tdc_multicast_copy.restype = C.c_int
+    lib.tdc_peer_copy.argtypes = [vp, vp, C.c_size_t, vp]
+    lib.tdc_peer_copy.restype = C.c_int
     for _n in ("tdc_layernorm", "tdc_attention", "tdc_residual_add"):
         getattr(lib, _n).restype = C.c_int
     lib.tdc_segment_workspace_bytes.argtypes = [i32, i64]

@@ -115,6 +115,13 @@ __device__ __forceinline__ void store16_mc(void* p, uint4 v) {
     *reinterpret_cast<uint4*>(p) = v;
 }
 
+// local memory -> multicast address, 16 bytes per thread and iteration
+__global__ void __launch_bounds__(512) multicast_copy_kernel(const uint4* __restrict__ src, uint4* dst, size_t n16) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    store16_mc<true>(dst + i, __ldg(src + i));
+}
+
 // static_out[c] = [ (side visual tokens, newline) x side | Ta audio tokens ]  in out_dtype (bf16 / fp16 / fp32).
 // One warp per token, 16-byte stores; kMulticast: stored through an NVSwitch multicast address, so the key frames'
 // pass-through tokens land on every GPU of the group while the kernel runs (the all-gather fused into the producer).
@@ -363,6 +370,22 @@ int pool_static_queries_launch(const __nv_bfloat16* xv, const float* newline, in
   pool_static_queries_kernel<<<static_cast<unsigned>(chunks * num_query), 256, 0, stream>>>(xv, newline, side, d,
                                                                                            num_query, out);
   return launched(err);
+}
+
+int multicast_copy_launch(const void* src, void* dst, size_t bytes, int ctas, cudaStream_t stream, const char** err) {
+  if (bytes == 0) return TDC_OK;
+  if (bytes % 16 != 0 || ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15)) {
+    if (err) *err = "multicast_copy: bytes and both pointers must be multiples of 16";
+    return TDC_EINVAL;
+  }
+  const size_t n16 = bytes / 16;
+  const unsigned blocks = static_cast<unsigned>(std::min<size_t>(ctas > 0 ? ctas : 16, (n16 + 511) / 512));
+  multicast_copy_kernel<<<blocks, 512, 0, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), n16);
+  if (cudaGetLastError() != cudaSuccess) {
+    if (err) *err = "multicast_copy launch failed";
+    return TDC_ECUDA;
+  }
+  return TDC_OK;
 }
 
 int assemble_static_launch(const __nv_bfloat16* xv, const __nv_bfloat16* xa, const float* newline, int chunks, int side,

@@ -1001,6 +1001,8 @@ int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* worksp
       const int rc = frames_static_batch(h, fc, w, c0, std::min<long long>(nb, a.n_chunks - c0), s);
       if (rc != TDC_OK) return rc;
     }
+  if (a.static_ready_event != nullptr && cudaEventRecord(static_cast<cudaEvent_t>(a.static_ready_event), s) != cudaSuccess)
+    return fail(h, TDC_ECUDA, "cudaEventRecord(static_ready_event) failed");
   if (a.rows == 0) return TDC_OK;
   // pass 2: dynamic frames
   const bool zero_map = fc.learned || fc.T > 0;
@@ -1211,6 +1213,31 @@ int tdc_combine_parts(const float* base, const float* parts, const float* logits
                                       static_cast<cudaStream_t>(stream), &err);
   if (rc != TDC_OK) g_create_error = err ? err : "tdc_combine_parts failed";
   return rc;
+}
+
+int tdc_multicast_copy(const void* src, void* dst_multicast, size_t bytes, int32_t ctas, tdc_stream_t stream) {
+  if (bytes == 0) return TDC_OK;
+  if (src == nullptr || dst_multicast == nullptr) {
+    g_create_error = "tdc_multicast_copy: null pointer";
+    return TDC_EINVAL;
+  }
+  const char* err = nullptr;
+  const int rc = multicast_copy_launch(src, dst_multicast, bytes, ctas, static_cast<cudaStream_t>(stream), &err);
+  if (rc != TDC_OK) g_create_error = err ? err : "tdc_multicast_copy failed";
+  return rc;
+}
+
+int tdc_peer_copy(const void* src, void* dst, size_t bytes, tdc_stream_t stream) {
+  if (bytes == 0) return TDC_OK;
+  if (src == nullptr || dst == nullptr) {
+    g_create_error = "tdc_peer_copy: null pointer";
+    return TDC_EINVAL;
+  }
+  if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)) != cudaSuccess) {
+    g_create_error = "tdc_peer_copy: cudaMemcpyAsync failed";
+    return TDC_ECUDA;
+  }
+  return TDC_OK;
 }
 
 int tdc_residual_add(const float* a, const float* b, float* out_f32, void* out_bf16, int64_t count,

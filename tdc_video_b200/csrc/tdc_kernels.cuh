@@ -112,6 +112,7 @@ int matvec_bias_launch(const __nv_bfloat16* w, const float* x, const float* b, f
 int pool_static_queries_launch(const __nv_bfloat16* xv, const float* newline, int chunks, int side, int d,
                                int num_query, __nv_bfloat16* out, cudaStream_t stream, const char** err);
 // static_out[c] = [(side visual tokens, newline) x side | ta audio tokens] (the key frame as it passes through)
+int multicast_copy_launch(const void* src, void* dst, size_t bytes, int ctas, cudaStream_t stream, const char** err);
 // (multicast: `out` is an NVSwitch multicast address, see l2_normalize_launch)
 int assemble_static_launch(const __nv_bfloat16* xv, const __nv_bfloat16* xa, const float* newline, int chunks, int side,
                            int ta, int d, void* out, int out_dtype, bool multicast, cudaStream_t stream,

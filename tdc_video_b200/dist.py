@@ -85,12 +85,62 @@ class MulticastGather:
         if not getattr(self.handle, "multicast_ptr", 0):
             raise RuntimeError("symmetric memory has no multicast mapping on this system")
         self.row_bytes = self.buf[0, 0].numel() * self.buf.element_size() if self.rows else 0
+        self.device = torch.device(device)
+        self._side: List[torch.cuda.Stream] = []
+        self._side_used = False
 
     def slot_ptr(self, row0: int = 0) -> int:
         """Multicast address of row `row0` of this rank's slot."""
         return int(self.handle.multicast_ptr) + (self.rank * self.rows + int(row0)) * self.row_bytes
 
+    def put_async(self, src: torch.Tensor, row0: int = 0, after: Optional[torch.cuda.Event] = None,
+                  mode: str = "dma", ctas: int = 16) -> None:
+        """Ship rows `src` (local, contiguous, the buffer's dtype) into rows [row0, row0 + len) of this rank's slot on
+        EVERY rank, on side streams, so that the transfer overlaps whatever the current stream does next.
+        mode "dma": one copy-engine transfer per peer (tdc_peer_copy into the peer's mapping of the symmetric buffer) —
+        takes no SM, the right tool beside persistent compute kernels; "multimem": tdc_multicast_copy (multimem.st from
+        `ctas` CTAs: one outbound copy, replicated by the switch).  `after`: event the side streams wait for (default:
+        everything enqueued on the current stream so far).  `barrier()` joins the side streams."""
+        from . import _lib
+        from .engine import _ptr
+        if src.dtype != self.buf.dtype or not src.is_contiguous():
+            raise ValueError("put_async needs a contiguous tensor of the buffer's dtype")
+        if tuple(src.shape[1:]) != self.tail or row0 < 0 or row0 + src.shape[0] > self.rows:
+            raise ValueError("put_async: rows do not fit the slot")
+        if mode not in ("dma", "multimem"):
+            raise ValueError('mode must be "dma" or "multimem"')
+        if not self._side:
+            self._side = [torch.cuda.Stream(self.device) for _ in range(min(self.world, 4))]
+        if after is None:
+            after = torch.cuda.Event()
+            after.record(torch.cuda.current_stream(self.device))
+        lib = _lib.load_library()
+        nbytes = src.numel() * src.element_size()
+        offset = (self.rank * self.rows + int(row0)) * self.row_bytes
+        with torch.cuda.device(self.device):
+            if mode == "multimem":
+                st = self._side[0]
+                st.wait_event(after)
+                src.record_stream(st)
+                rc = lib.tdc_multicast_copy(_ptr(src), int(self.handle.multicast_ptr) + offset, nbytes, int(ctas),
+                                            st.cuda_stream)
+                _lib.check(rc, None, "tdc_multicast_copy")
+            else:
+                ptrs = self.handle.buffer_ptrs
+                for i in range(self.world):
+                    peer = (self.rank + i) % self.world      # start with the local copy, then a different peer per rank
+                    st = self._side[i % len(self._side)]
+                    st.wait_event(after)
+                    src.record_stream(st)
+                    rc = lib.tdc_peer_copy(_ptr(src), int(ptrs[peer]) + offset, nbytes, st.cuda_stream)
+                    _lib.check(rc, None, "tdc_peer_copy")
+        self._side_used = True
+
     def barrier(self) -> None:
+        if self._side_used:
+            for st in self._side:
+                torch.cuda.current_stream(self.device).wait_stream(st)
+            self._side_used = False
         self.handle.barrier()
 
     @property

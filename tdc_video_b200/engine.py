@@ -72,6 +72,14 @@ def range_plan(chunk_start, chunk_len, a: int, b: int, keep_static: bool = True)
     return f0, f1, st, rf, rck
 
 
+def _raw_event(ev: torch.cuda.Event, device) -> int:
+    """cudaEvent_t of a torch event (torch creates it lazily at the first record)."""
+    if not ev.cuda_event:
+        with torch.cuda.device(device):
+            ev.record()
+    return int(ev.cuda_event)
+
+
 class QFormerEngine:
     """Owns one `tdc_handle` (re-packed bf16 weights on one GPU) and a growable workspace."""
 
@@ -286,7 +294,8 @@ class QFormerEngine:
                         input_ids: Optional[torch.Tensor] = None, num_query: int = 16, learned_queries: bool = False,
                         fold: bool = True, want_static: bool = True, out_dtype=torch.bfloat16,
                         multicast_ptr: Optional[int] = None, layer0_dedup: bool = True,
-                        chunk_prompt: Optional[torch.Tensor] = None, static_multicast_ptr: Optional[int] = None):
+                        chunk_prompt: Optional[torch.Tensor] = None, static_multicast_ptr: Optional[int] = None,
+                        static_ready_event: Optional[torch.cuda.Event] = None):
         """The TDC stage from the towers' outputs (tdc_compress_frames): mm_projector, image_newline, audio_proj,
         query build, Q-Former, vision_proj + L2-normalise for all chunks of a video in one call.
 
@@ -341,7 +350,8 @@ class QFormerEngine:
                           int(not layer0_dedup), static_ptr,
                           int(multicast_ptr) if multicast_ptr is not None else out.data_ptr(),
                           None if cp is None else cp.data_ptr(), 0 if ids is None else int(ids.shape[0]),
-                          int(static_multicast_ptr is not None))
+                          int(static_multicast_ptr is not None),
+                          None if static_ready_event is None else _raw_event(static_ready_event, dev))
         with torch.cuda.device(dev):
             rc = self.lib.tdc_compress_frames(self._h, C.byref(a), _ptr(ws), ws.numel(), _stream(dev))
         check(rc, self._h, "tdc_compress_frames")
