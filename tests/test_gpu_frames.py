@@ -259,3 +259,31 @@ def test_several_videos_with_their_own_prompts_in_one_call():
             alone = comp.compress_video_from_towers(v["tower_features"], v["segment_sizes"], input_ids=v["input_ids"],
                                                     audio_frames=v["audio_frames"])
             assert torch.equal(got, alone), query_type
+
+
+def test_key_frames_ready_event_lets_a_side_stream_ship_them_early():
+    """tdc_frames_args.static_ready_event is recorded once the key frames' tokens are complete; a side stream that
+    waits for it copies them with the copy engines (tdc_peer_copy) while the rows are still being compressed.  The
+    copy equals static_out and the compressed tokens are unchanged by the extra event."""
+    import ctypes as C
+    from tdc_video_b200 import _lib
+    geom, sd, frames, aud, sizes = _full_problem(17, 40, 4)
+    eng = _engine(geom, sd, 1024, True)
+    p, sf, rf, rc = _plan(sizes)
+    x, a = torch.from_numpy(frames).cuda().bfloat16(), torch.from_numpy(aud).cuda().bfloat16()
+    st0, comp0 = eng.compress_frames(x, sf, rf, rc, audio=a)
+    ev = torch.cuda.Event()
+    side = torch.cuda.Stream()
+    st1, comp1 = eng.compress_frames(x, sf, rf, rc, audio=a, static_ready_event=ev)
+    shipped = torch.zeros_like(st1)
+    side.wait_event(ev)
+    lib = _lib.load_library()
+    rc_ = lib.tdc_peer_copy(C.c_void_p(st1.data_ptr()), C.c_void_p(shipped.data_ptr()),
+                            st1.numel() * st1.element_size(), C.c_void_p(side.cuda_stream))
+    assert rc_ == 0
+    side.synchronize()
+    assert torch.equal(shipped, st0)
+    torch.cuda.synchronize()
+    assert torch.equal(st1, st0) and torch.equal(comp1, comp0)
+    assert lib.tdc_peer_copy(None, C.c_void_p(shipped.data_ptr()), 16, None) == -1
+    assert lib.tdc_multicast_copy(C.c_void_p(st1.data_ptr()), C.c_void_p(shipped.data_ptr() + 8), 32, 0, None) == -1

@@ -1,4 +1,5 @@
-"""torchrun check: tdc_compress_multicast delivers every rank's rows to all ranks (== NCCL all-gather)."""
+"""torchrun check: tdc_compress_multicast delivers every rank's rows to all ranks (== NCCL all-gather), and so do
+MulticastGather.put_async's copy-engine (tdc_peer_copy) and multimem (tdc_multicast_copy) modes."""
 import os
 import sys
 
@@ -38,6 +39,20 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"mcast_check world={world}: multicast gather == NCCL all-gather: {bool(flag.item())}")
+    # put_async: local rows -> every rank's buffer on side streams (copy engines / multimem copy kernel)
+    for mode in ("dma", "multimem"):
+        mg.buf.zero_()
+        dist.barrier()
+        torch.cuda.synchronize()
+        mg.put_async(local_out[:20], 0, mode=mode)
+        mg.put_async(local_out[20:].contiguous(), 20, mode=mode)
+        mg.barrier()
+        torch.cuda.synchronize()
+        f2 = torch.tensor([int(torch.equal(mg.gathered, ref))], device=dev)
+        dist.all_reduce(f2, op=dist.ReduceOp.MIN)
+        flag = torch.minimum(flag, f2)
+        if rank == 0:
+            print(f"mcast_check world={world}: put_async(mode={mode}) == NCCL all-gather: {bool(f2.item())}")
     dist.destroy_process_group()
     sys.exit(0 if flag.item() else 1)
 
