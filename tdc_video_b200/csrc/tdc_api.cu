@@ -992,6 +992,10 @@ int tdc_compress_frames(tdc_handle* h, const tdc_frames_args* args, void* worksp
     while (nb > 0 && need(nb) > workspace_bytes) --nb;
     if (nb <= 0) return fail(h, TDC_EWORKSPACE, "workspace too small for a single row; see tdc_frames_workspace_bytes");
   }
+  if (const char* cap = std::getenv("TDC_FRAMES_BATCH")) {   // dev knob: cap the internal batch (rows / key frames)
+    const long long v = std::atoll(cap);
+    if (v > 0) nb = std::min(nb, v);
+  }
   FramesWorkspace w = carve_frames(h, static_cast<uint8_t*>(workspace), a.n_chunks, a.rows, nb, fc.Tv, fc.Ta, fc.side,
                                    fc.K, fc.T, fold);
 
