@@ -274,8 +274,9 @@ def test_key_frames_ready_event_lets_a_side_stream_ship_them_early():
     st0, comp0 = eng.compress_frames(x, sf, rf, rc, audio=a)
     ev = torch.cuda.Event()
     side = torch.cuda.Stream()
+    shipped = torch.zeros_like(st0)
+    torch.cuda.synchronize()          # (the side stream below is ordered after `ev` only, not after this fill)
     st1, comp1 = eng.compress_frames(x, sf, rf, rc, audio=a, static_ready_event=ev)
-    shipped = torch.zeros_like(st1)
     side.wait_event(ev)
     lib = _lib.load_library()
     rc_ = lib.tdc_peer_copy(C.c_void_p(st1.data_ptr()), C.c_void_p(shipped.data_ptr()),
