@@ -110,9 +110,35 @@ def main():
         torch.cuda.synchronize()
         walls2.append((time.perf_counter() - t0) * 1e3)
         devs2.append(e0.elapsed_time(e1))
+    # tdc_compress_frames alone on that video's plan: eager launches vs one CUDA-graph replay (the call is
+    # stream-ordered and makes no host reads, so it captures as is)
+    from tdc_video_b200.compressor import plan_chunks
+    pl = plan_chunks([9] * 24 + [8], True)
+    i32 = lambda a: torch.from_numpy(a.astype(np.int32)).to(dev)
+    sf, rf, rc = i32(pl.static_frames), i32(pl.row_frames), i32(pl.row_chunk)
+    aud = (torch.randn(n, 50, 768, device=dev, generator=g0) * 0.5).to(torch.bfloat16)
+    eng2 = comp2._frames_engine()
+    call = lambda: eng2.compress_frames(feats, sf, rf, rc, audio=aud, input_ids=ids, num_query=16)
+    f_eager_dev, f_eager_wall = timed(call)
+    l0 = eng2.launch_count()
+    ref_static, ref_out = call()
+    launches = eng2.launch_count() - l0
+    g2 = torch.cuda.CUDAGraph()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g2, stream=side):
+            cap_static, cap_out = call()
+    torch.cuda.current_stream().wait_stream(side)
+    f_graph_dev, f_graph_wall = timed(g2.replay)
+    torch.cuda.synchronize()
+    frames_call = {"rows": int(pl.num_rows), "chunks": int(pl.num_chunks), "kernel_launches": int(launches),
+                   "eager_ms": f_eager_dev, "eager_wall_ms": f_eager_wall, "graph_ms": f_graph_dev,
+                   "graph_wall_ms": f_graph_wall,
+                   "graph_equals_eager": bool(torch.equal(cap_out, ref_out) and torch.equal(cap_static, ref_static))}
     from_towers = {"wall_ms_median": float(np.median(walls2)), "device_ms_median": float(np.median(devs2)),
                    "output_tokens": int(out2.shape[0]), "finite": bool(torch.isfinite(out2.float()).all()),
-                   "includes": "mm_projector on 224 frames (1.07 TFLOP), newline, audio_proj, query build"}
+                   "includes": "mm_projector on 224 frames (1.07 TFLOP), newline, audio_proj, query build",
+                   "tdc_compress_frames_alone": frames_call}
     print(json.dumps({
         "metric": "TDC stage latency, one 224-frame video (Qwen2-7B widths, L=206, K=16, T=32, audio)",
         "wall_ms_median": float(np.median(walls)), "wall_ms_min": float(min(walls)),
