@@ -288,3 +288,32 @@ def test_key_frames_ready_event_lets_a_side_stream_ship_them_early():
     assert torch.equal(st1, st0) and torch.equal(comp1, comp0)
     assert lib.tdc_peer_copy(None, C.c_void_p(shipped.data_ptr()), 16, None) == -1
     assert lib.tdc_multicast_copy(C.c_void_p(st1.data_ptr()), C.c_void_p(shipped.data_ptr() + 8), 32, 0, None) == -1
+
+
+def test_frames_entry_captures_into_a_cuda_graph():
+    """The header's contract: stream-ordered, no host reads of device data -> the whole call replays from a CUDA graph
+    with the same bits, also after the inputs changed in place."""
+    geom, sd, frames, aud, sizes = _full_problem(23, 36, 4)
+    eng = _engine(geom, sd, 1024, True)
+    p, sf, rf, rc = _plan(sizes)
+    sf, rf, rc = sf.cuda(), rf.cuda(), rc.cuda()
+    x, a = torch.from_numpy(frames).cuda().bfloat16(), torch.from_numpy(aud).cuda().bfloat16()
+    st0, comp0 = eng.compress_frames(x, sf, rf, rc, audio=a)          # also sizes the workspace
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            st1, comp1 = eng.compress_frames(x, sf, rf, rc, audio=a)
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(st1, st0) and torch.equal(comp1, comp0)
+    x2 = torch.roll(x, 5, dims=0).contiguous()
+    st2, comp2 = eng.compress_frames(x2, sf, rf, rc, audio=a)
+    torch.cuda.synchronize()
+    x.copy_(x2)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(st1, st2) and torch.equal(comp1, comp2) and not torch.equal(comp2, comp0)
