@@ -317,3 +317,19 @@ def test_frames_entry_captures_into_a_cuda_graph():
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(st1, st2) and torch.equal(comp1, comp2) and not torch.equal(comp2, comp0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_frames_entry_16_bit_outputs_are_the_rounded_fp32_outputs(dtype):
+    """I/O in bf16 and in fp16 (the reference's inference dtype, builder.py:69).  The 16-bit outputs are the
+    fp32 outputs rounded once (same kernels, only the final stores differ)."""
+    geom, sd, frames, aud, sizes = _full_problem(29, 14, 4)
+    eng = _engine(geom, sd, 1024, True)
+    p, sf, rf, rc = _plan(sizes)
+    x, a = torch.from_numpy(frames).cuda().to(dtype), torch.from_numpy(aud).cuda().to(dtype)
+    st32, c32 = eng.compress_frames(x, sf, rf, rc, audio=a, out_dtype=torch.float32)
+    st16, c16 = eng.compress_frames(x, sf, rf, rc, audio=a, out_dtype=dtype)
+    torch.cuda.synchronize()
+    assert st16.dtype == dtype and c16.dtype == dtype
+    assert torch.equal(c16, c32.to(dtype))
+    assert torch.equal(st16, st32.to(dtype))
