@@ -490,9 +490,7 @@ def bench_frames(args, w, ctx):
         st, rf, rc = plan
         so, out = eng.compress_frames(frames_dev, st, rf, rc, audio=audio_dev, input_ids=ids_dev, num_query=K,
                                       fold=use_fold, want_static=want_static, out_dtype=torch.bfloat16,
-                                      multicast_ptr=mc_ptr)
-        if want_static:
-            static_out[c0:c1].copy_(so)
+                                      multicast_ptr=mc_ptr, static_into=static_out[c0:c1] if want_static else None)
         return out
 
     def make_step(chunks, plans_, mc, gath, chunk0=0, use_fold=True):

@@ -295,7 +295,8 @@ class QFormerEngine:
                         fold: bool = True, want_static: bool = True, out_dtype=torch.bfloat16,
                         multicast_ptr: Optional[int] = None, layer0_dedup: bool = True,
                         chunk_prompt: Optional[torch.Tensor] = None, static_multicast_ptr: Optional[int] = None,
-                        static_ready_event: Optional[torch.cuda.Event] = None):
+                        static_ready_event: Optional[torch.cuda.Event] = None,
+                        static_into: Optional[torch.Tensor] = None, out_into: Optional[torch.Tensor] = None):
         """The TDC stage from the towers' outputs (tdc_compress_frames): mm_projector, image_newline, audio_proj,
         query build, Q-Former, vision_proj + L2-normalise for all chunks of a video in one call.
 
@@ -303,6 +304,8 @@ class QFormerEngine:
         static_frames [C] / row_frames [R] / row_chunk [R] int32 (see compressor.plan_chunks).
         input_ids [1, T] (one prompt for all rows) or [P, T] with chunk_prompt [C] int32 (prompt of every chunk:
         several videos with their own questions in one call).
+        `static_into` / `out_into`: contiguous destinations ([C, side*(side+1)+Ta, d] / [R, K, d], e.g. slices of a
+        whole-video buffer) the library writes directly instead of fresh tensors.
         Returns (static_out [C, side*(side+1)+Ta, d] or None, compressed [R, K, d])."""
         if self.cfg.d_frame_in <= 0:
             raise RuntimeError("engine was created without d_frame_in: no upstream entry")
@@ -334,13 +337,25 @@ class QFormerEngine:
             raise ValueError("several prompts need chunk_prompt")
         side = int(round(Tv ** 0.5))
         d = self.cfg.d_out
+        def dest(t, shape, what):
+            if tuple(t.shape) != shape or t.dtype != out_dtype or t.device != dev or not t.is_contiguous():
+                raise ValueError(f"{what} must be a contiguous {shape} {out_dtype} tensor on {dev}")
+            return t
+
         static_out = None
-        if want_static and static_multicast_ptr is None:
+        if static_into is not None and static_multicast_ptr is None:
+            static_out = dest(static_into, (C_, side * (side + 1) + Ta, d), "static_into")
+        elif want_static and static_multicast_ptr is None:
             static_out = torch.empty((C_, side * (side + 1) + Ta, d), dtype=out_dtype, device=dev)
         static_ptr = None if static_out is None else static_out.data_ptr()
         if static_multicast_ptr is not None:     # the key frames' tokens go to a caller-owned multicast mapping
             static_ptr = int(static_multicast_ptr)
-        out = None if multicast_ptr is not None else torch.empty((R, num_query, d), dtype=out_dtype, device=dev)
+        if multicast_ptr is not None:
+            out = None
+        elif out_into is not None:
+            out = dest(out_into, (R, num_query, d), "out_into")
+        else:
+            out = torch.empty((R, num_query, d), dtype=out_dtype, device=dev)
         if C_ == 0 and R == 0:
             return static_out, out
         ws = self._frames_workspace(C_, R, Tv, Ta, num_query, T)
@@ -408,6 +423,9 @@ class QFormerEngine:
             n_st, n_rf = len(p[2]), len(p[3])
             offs.append((o, o + n_st, o + n_st + n_rf, o + n_st + 2 * n_rf))
             o += n_st + 2 * n_rf
+        # destinations the library can write in place (same dtype, contiguous, on this device); else a copy per range
+        fits = lambda t: t is not None and t.dtype == out_host.dtype and t.device == dev and t.is_contiguous()
+        direct_static, direct_out = fits(static_out), fits(out_device)
         self._h2d_stream.wait_stream(cur)
         for i, (a, b) in enumerate(bounds):
             sb = i % 2
@@ -422,15 +440,17 @@ class QFormerEngine:
                     stage_a[sb][: f1 - f0].copy_(audio_host[f0:f1], non_blocking=True)
                 h2d_done[sb].record(self._h2d_stream)
             cur.wait_event(h2d_done[sb])
+            r0, r1 = int(row_base[a]), int(row_base[b])
             s_out, comp = self.compress_frames(stage_f[sb][: f1 - f0], plan_dev[0], plan_dev[1], plan_dev[2],
                                                audio=None if stage_a is None else stage_a[sb][: f1 - f0],
                                                input_ids=ids_dev, num_query=K, learned_queries=learned_queries,
                                                fold=fold, want_static=static_out is not None,
-                                               out_dtype=out_host.dtype)
-            r0, r1 = int(row_base[a]), int(row_base[b])
-            if static_out is not None:
+                                               out_dtype=out_host.dtype,
+                                               static_into=static_out[a:b] if direct_static else None,
+                                               out_into=out_device[r0:r1] if direct_out else None)
+            if static_out is not None and not direct_static:
                 static_out[a:b].copy_(s_out)
-            if out_device is not None:
+            if out_device is not None and not direct_out:
                 out_device[r0:r1].copy_(comp)
             compute_done[sb].record(cur)
             with torch.cuda.stream(self._d2h_stream):

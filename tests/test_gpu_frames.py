@@ -333,3 +333,25 @@ def test_frames_entry_16_bit_outputs_are_the_rounded_fp32_outputs(dtype):
     assert st16.dtype == dtype and c16.dtype == dtype
     assert torch.equal(c16, c32.to(dtype))
     assert torch.equal(st16, st32.to(dtype))
+
+
+def test_outputs_written_in_place_into_caller_buffers():
+    """static_into / out_into: the library writes the key-frame and compressed tokens straight into slices of a
+    whole-video buffer (no fresh tensors, no extra device copy); bad destinations are rejected."""
+    geom, sd, frames, aud, sizes = _full_problem(31, 20, 4)
+    eng = _engine(geom, sd, 1024, True)
+    p, sf, rf, rc = _plan(sizes)
+    x, a = torch.from_numpy(frames).cuda().bfloat16(), torch.from_numpy(aud).cuda().bfloat16()
+    st0, c0 = eng.compress_frames(x, sf, rf, rc, audio=a)
+    big_s = torch.zeros((st0.shape[0] + 3,) + tuple(st0.shape[1:]), dtype=torch.bfloat16, device="cuda")
+    big_c = torch.zeros((c0.shape[0] + 5,) + tuple(c0.shape[1:]), dtype=torch.bfloat16, device="cuda")
+    st1, c1 = eng.compress_frames(x, sf, rf, rc, audio=a, static_into=big_s[2:2 + st0.shape[0]],
+                                  out_into=big_c[4:4 + c0.shape[0]])
+    torch.cuda.synchronize()
+    assert st1.data_ptr() == big_s[2:].data_ptr() and c1.data_ptr() == big_c[4:].data_ptr()
+    assert torch.equal(big_s[2:2 + st0.shape[0]], st0) and torch.equal(big_c[4:4 + c0.shape[0]], c0)
+    assert not big_s[:2].any() and not big_s[2 + st0.shape[0]:].any() and not big_c[:4].any()
+    with pytest.raises(ValueError):
+        eng.compress_frames(x, sf, rf, rc, audio=a, out_into=big_c)                       # wrong row count
+    with pytest.raises(ValueError):
+        eng.compress_frames(x, sf, rf, rc, audio=a, static_into=big_s[2:2 + st0.shape[0]].float())   # wrong dtype
