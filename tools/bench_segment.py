@@ -27,7 +27,9 @@ def main():
     sel, seg, cos = adapt_segment(feats, 24)
     torch.cuda.synchronize()
     sel_o, seg_o, cos_o = driver_oracle.adapt_segment(feats.float().cpu(), 24)
-    ok = torch.equal(seg.cpu(), seg_o) and torch.allclose(cos.cpu(), cos_o, atol=1e-3)
+    # the library rounds the similarities to the feature dtype (bf16: half an ulp below 1.0 = 2e-3), as the reference's
+    # F.cosine_similarity on bf16 features does; the oracle keeps fp32
+    ok = torch.equal(seg.cpu(), seg_o) and torch.allclose(cos.cpu(), cos_o, atol=3e-3)
     for _ in range(3):
         adapt_segment(feats, 24)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
