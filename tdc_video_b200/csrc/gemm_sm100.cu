@@ -52,7 +52,8 @@ struct EpilogueArgs {
   int mode;
   int slab_cols;  // output columns per slab (== N for a plain matrix)
   unsigned long long hint_a, hint_w, hint_c;  // L2 eviction policies of the A / W loads and the C stores
-  int debug_skip;  // dev knob (TDC_GEMM_DEBUG): 1 = drain TMEM but skip the epilogue math + stores
+  int debug_skip;  // dev knob (TDC_GEMM_DEBUG): 1 = drain TMEM but skip the epilogue math + stores, 2 = skip the TMA
+                   // stores only, 3 = skip the math / shared-memory staging only
 };
 
 template <int CG, int BLOCK_N, int STAGES>
@@ -302,14 +303,14 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           tmem_ld_32x32(t_addr + c * 32, v);
           load_bias32(epi.bias, col0, n, bias);
           tmem_ld_wait();
-          if (live && col0 < n && !epi.debug_skip) {
+          if (live && col0 < n && epi.debug_skip != 1) {
             if (lane == 0) tma_store_wait_read<kStoreBufs - 1>();  // staging[sbuf] no longer being read
             __syncwarp();
             uint8_t* tile_buf = staging + sbuf * kStoreTileBytes;
-            stage_32_columns<EPI_BIAS_F32>(v, tile_buf, lane, 0, bias);
+            if (epi.debug_skip != 3) stage_32_columns<EPI_BIAS_F32>(v, tile_buf, lane, 0, bias);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && epi.debug_skip != 2) {
               tma_store_3d(&map_c, tile_buf, col0 % epi.slab_cols, row0, col0 / epi.slab_cols, epi.hint_c);
               tma_store_commit();
             }
@@ -328,11 +329,13 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           load_bias32(epi.bias, col0, n, bias0);
           load_bias32(epi.bias, col0 + 32, n, bias1);
           tmem_ld_wait();
-          if (live && col0 < n && !epi.debug_skip) {
+          if (live && col0 < n && epi.debug_skip != 1) {
             if (lane == 0) tma_store_wait_read<kStoreBufs - 1>();
             __syncwarp();
             uint8_t* tile_buf = staging + sbuf * kStoreTileBytes;
-            if (epi.mode == EPI_BIAS_GELU_BF16) {
+            if (epi.debug_skip == 3) {
+              // dev knock-out: stores only (stale staging contents)
+            } else if (epi.mode == EPI_BIAS_GELU_BF16) {
               stage_32_columns<EPI_BIAS_GELU_BF16>(v0, tile_buf, lane, 0, bias0);
               stage_32_columns<EPI_BIAS_GELU_BF16>(v1, tile_buf, lane, 4, bias1);
             } else {
@@ -341,7 +344,7 @@ tdc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && epi.debug_skip != 2) {
               tma_store_3d(&map_c, tile_buf, col0 % epi.slab_cols, row0, col0 / epi.slab_cols, epi.hint_c);
               tma_store_commit();
             }
@@ -544,7 +547,8 @@ int launch_variant(const GemmProblem& p, cudaStream_t stream, const char** err) 
   auto pick = [](char ch, unsigned long long dflt) -> unsigned long long {
     return ch == 'n' ? kL2EvictNormal : ch == 'f' ? kL2EvictFirst : ch == 'l' ? kL2EvictLast : dflt;
   };
-  static const int debug_skip_epilogue = [] { const char* e = getenv("TDC_GEMM_DEBUG"); return (e && atoi(e) == 1) ? 1 : 0; }();
+  // dev knock-outs (wrong results by design): 1 = drain TMEM only, 2 = no TMA stores, 3 = stores without the math
+  static const int debug_skip_epilogue = [] { const char* e = getenv("TDC_GEMM_DEBUG"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 3) ? v : 0; }();
   const bool he = hints_env != nullptr && strlen(hints_env) == 3;
   EpilogueArgs e{p.bias, p.mode, p.slab_cols > 0 ? p.slab_cols : p.n,
                  pick(he ? hints_env[0] : 0, kL2EvictNormal), pick(he ? hints_env[1] : 0, kL2EvictLast),
