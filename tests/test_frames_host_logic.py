@@ -51,3 +51,28 @@ def test_frames_flop_accounting():
     assert abs(model / 1e9 - 70.35) < 0.01 and abs(executed / 1e9 - 48.26) < 0.01
     assert kv_exec == 3 * (2 * 144 * 3584 + 2 * 50 * 768) * 9216
     assert executed < model and kv_exec < 3 * f_row_kv
+
+
+def test_range_plans_of_random_videos_tile_the_global_plan():
+    """Property: for any segment sizes and any range size (with or without the head / tail tapers), the per-range
+    plans handed to tdc_compress_frames are exactly the global plan cut at chunk boundaries."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(1, 30), min_size=1, max_size=25), st.integers(1, 40), st.booleans(), st.booleans())
+    def check(sizes, cb, head, tail):
+        p = plan_chunks(sizes, True)
+        bounds = plan_chunk_ranges(p.num_chunks, cb, taper_tail=tail, taper_head=head)
+        assert bounds[0][0] == 0 and bounds[-1][1] == p.num_chunks
+        rows, statics, chunk_of_row = [], [], []
+        for a, b in bounds:
+            f0, f1, stt, rf, rck = range_plan(p.static_frames, p.chunk_len, a, b)
+            assert 0 <= f0 < f1 <= sum(sizes) and (stt >= 0).all() and (rf < f1 - f0).all()
+            statics.append(stt + f0)
+            rows.append(rf + f0)
+            chunk_of_row.append(rck + a)
+        assert np.array_equal(np.concatenate(statics), p.static_frames)
+        assert np.array_equal(np.concatenate(rows), p.row_frames)
+        assert np.array_equal(np.concatenate(chunk_of_row), p.row_chunk)
+
+    check()
